@@ -1,0 +1,264 @@
+// formats.cuh -- kernel-native tile layouts of the quantized weight formats.
+//
+// Device layout (DESIGN.md "Data layout in HBM"): a logical [N,K] weight is cut into tiles of
+// TILE_ROWS=128 rows x CHUNK_K=256 k ("chunks"), stored tile-row-major then k-chunk-major, each chunk one
+// contiguous, 16-byte aligned byte string that a single cp.async.bulk (TMA) copy brings into shared memory.
+// Inside a chunk the canonical ggml block is split into SoA planes over the 128 rows (so 210-byte Q6_K and
+// 34-byte Q8_0 blocks become 16-byte aligned without padding: device bytes == canonical bytes), the 4/6-bit
+// payload is re-ordered so that one 16-byte "unit" holds 32 consecutive k of one row (low nibbles = first 16,
+// high nibbles = last 16), and 16-byte units are XOR-swizzled by the row index so that BOTH access patterns
+// are bank-conflict free:  (a) dp4a matvec: 8 lanes x 16 B walk one row (b) tcgen05 GEMM: thread == row.
+//
+// Every format exposes the same micro-interface:
+//   repack_row(src canonical bytes of this row's 256 k, n_valid, chunk, r, meta)   one-off at upload
+//   load_unit<SMEM>(chunk, r, i, Unit&, meta)    -> 32 integer weights (as 8 packed byte words) of unit i
+//        plus the affine map  W = a[h] * (v - off[h]) - b[h]   for the two 16-element halves h.
+// which is the decomposition the oracle uses (oracle/quant_oracle.c decompose_block), so dequantized weights
+// and integer partials are bit-comparable.
+#pragma once
+#include "common.cuh"
+
+namespace b200q {
+
+struct Unit {
+    uint32_t v[8];  // v[k] byte c = integer weight of element 4k+c of the unit (k<4: first half, k>=4: second half)
+    float a[2], b[2];
+    int off[2];
+};
+
+struct FmtMeta {
+    int gpc;  // AWQ/GPTQ: scale groups per 256-k chunk (1,2,4,8); unused otherwise
+};
+
+template <bool SMEM>
+__device__ __forceinline__ uint4 ld16(const uint8_t* p) {
+    if constexpr (SMEM) return lds128(p);
+    else return *reinterpret_cast<const uint4*>(p);
+}
+template <bool SMEM>
+__device__ __forceinline__ uint2 ld8(const uint8_t* p) {
+    if constexpr (SMEM) return lds64(p);
+    else return *reinterpret_cast<const uint2*>(p);
+}
+__device__ __forceinline__ uint32_t ld4(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ uint16_t ld2(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+
+__device__ __forceinline__ int swz8(int r, int u) { return u ^ (r & 7); }          // planes with >= 128 B per row
+__device__ __forceinline__ int swz4(int r, int u) { return u ^ ((r >> 1) & 3); }   // planes with 64 B per row
+
+// Q4_K / Q5_K 6-bit scale+min unpack from the canonical 12 bytes
+__device__ __forceinline__ void k4_scale_min(int j, const uint8_t* s, int& sc, int& m) {
+    if (j < 4) {
+        sc = s[j] & 63;
+        m = s[j + 4] & 63;
+    } else {
+        sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4);
+        m = (s[j + 4] >> 4) | ((s[j] >> 6) << 4);
+    }
+}
+
+// write 32 4-bit values q[0..31] as one 16-byte unit: byte b = q[b] | q[16+b] << 4
+__device__ __forceinline__ void store_nib_unit(uint8_t* dst, const uint8_t* q) {
+#pragma unroll
+    for (int b = 0; b < 16; b++) dst[b] = (uint8_t)((q[b] & 0xF) | ((q[16 + b] & 0xF) << 4));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q4_K : canonical [f16 d][f16 dmin][u8 s[12]][u8 qs[128]]  (144 B / 256)
+// chunk: QS plane 128 rows x 128 B | HDR plane 128 rows x 16 B: [f16 d][f16 dmin][sc'|m' 12 B]
+//   sc'/m' re-encoding (same 12 bytes, lane-uniform extraction): byte j = sc_j | (m_j & 3) << 6 (j<8),
+//   byte 8 + j/2 nibble j%2 = m_j >> 2.
+// ------------------------------------------------------------------------------------------------
+struct FmtQ4K {
+    static constexpr int FAMILY = 1, SUB = 32;
+    static constexpr bool HAS_MIN = true;
+    static constexpr int QS = 0, HDR = 128 * 128;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 144; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 144; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* qs = chunk + QS + r * 128;
+        uint8_t* hdr = chunk + HDR + r * 16;
+        if (nvalid <= 0) {
+            for (int j = 0; j < 128; j++) qs[j] = 0;
+            for (int j = 0; j < 16; j++) hdr[j] = 0;
+            return;
+        }
+        for (int j = 0; j < 4; j++) hdr[j] = src[j];
+        const uint8_t* s = src + 4;
+        const uint8_t* q = src + 16;
+        int sc[8], m[8];
+        for (int j = 0; j < 8; j++) k4_scale_min(j, s, sc[j], m[j]);
+        for (int j = 0; j < 8; j++) hdr[4 + j] = (uint8_t)(sc[j] | ((m[j] & 3) << 6));
+        for (int j = 0; j < 4; j++) hdr[12 + j] = (uint8_t)((m[2 * j] >> 2) | ((m[2 * j + 1] >> 2) << 4));
+        for (int i = 0; i < 8; i++) {  // unit i == sub-block i: chunk c = i/2, high nibble iff i odd
+            uint8_t v[32];
+            int c = i >> 1, hi = i & 1;
+            for (int l = 0; l < 32; l++) v[l] = hi ? (q[32 * c + l] >> 4) : (q[32 * c + l] & 0xF);
+            store_nib_unit(qs + 16 * swz8(r, i), v);
+        }
+    }
+    template <bool SMEM>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
+        u.v[0] = w.x & 0x0F0F0F0Fu; u.v[1] = w.y & 0x0F0F0F0Fu; u.v[2] = w.z & 0x0F0F0F0Fu; u.v[3] = w.w & 0x0F0F0F0Fu;
+        u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
+        u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        const uint8_t* hdr = chunk + HDR + r * 16;
+        uint32_t dd = ld4(hdr);
+        float d = half_bits_to_float((uint16_t)(dd & 0xFFFF)), dmin = half_bits_to_float((uint16_t)(dd >> 16));
+        uint32_t b1 = hdr[4 + i], b2 = hdr[12 + (i >> 1)];
+        int sc = b1 & 63;
+        int m = (b1 >> 6) | (((b2 >> (4 * (i & 1))) & 0xF) << 2);
+        u.a[0] = u.a[1] = __fmul_rn(d, (float)sc);
+        u.b[0] = u.b[1] = __fmul_rn(dmin, (float)m);
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Q6_K : canonical [u8 ql[128]][u8 qh[64]][i8 sc[16]][f16 d]  (210 B / 256)
+// chunk: QL 128x128 B (low 4 bits, unit order) | QH 128x64 B | SC 128x16 B | D 128x2 B
+//   qh' unit i = 2 words: word h serves elements 32i+16h+e (e<16): bits [8(e%4)+2(e/4) .. +1] = v>>4
+// ------------------------------------------------------------------------------------------------
+struct FmtQ6K {
+    static constexpr int FAMILY = 2, SUB = 16;
+    static constexpr bool HAS_MIN = false;
+    static constexpr int QL = 0, QH = 128 * 128, SC = QH + 128 * 64, D = SC + 128 * 16;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 210; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 210; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* ql = chunk + QL + r * 128;
+        uint8_t* qh = chunk + QH + r * 64;
+        uint8_t* sc = chunk + SC + r * 16;
+        uint8_t* dd = chunk + D + r * 2;
+        if (nvalid <= 0) {
+            for (int j = 0; j < 128; j++) ql[j] = 0;
+            for (int j = 0; j < 64; j++) qh[j] = 0;
+            for (int j = 0; j < 16; j++) sc[j] = 0;
+            dd[0] = dd[1] = 0;
+            return;
+        }
+        const uint8_t* L0 = src; const uint8_t* H0 = src + 128;
+        for (int j = 0; j < 16; j++) sc[j] = src[192 + j];
+        dd[0] = src[208]; dd[1] = src[209];
+        for (int i = 0; i < 8; i++) {
+            uint8_t v[32];
+            for (int l = 0; l < 32; l++) {
+                int e = 32 * i + l, h = e >> 7, rr = (e & 127) >> 5, ll = e & 31;
+                const uint8_t* L = L0 + 64 * h; const uint8_t* H = H0 + 32 * h;
+                int lo = (rr & 1) ? L[ll + 32] : L[ll];
+                lo = (rr & 2) ? (lo >> 4) : (lo & 15);
+                int hi = (H[ll] >> (2 * rr)) & 3;
+                v[l] = (uint8_t)(lo | (hi << 4));
+            }
+            store_nib_unit(ql + 16 * swz8(r, i), v);
+            uint32_t w[2] = {0u, 0u};
+            for (int h = 0; h < 2; h++)
+                for (int e = 0; e < 16; e++) w[h] |= (uint32_t)(v[16 * h + e] >> 4) << (8 * (e & 3) + 2 * (e >> 2));
+            uint8_t* dst = qh + 16 * swz4(r, i >> 1) + 8 * (i & 1);
+            for (int h = 0; h < 2; h++)
+                for (int c = 0; c < 4; c++) dst[4 * h + c] = (uint8_t)(w[h] >> (8 * c));
+        }
+    }
+    template <bool SMEM>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w = ld16<SMEM>(chunk + QL + r * 128 + 16 * swz8(r, i));
+        uint2 hq = ld8<SMEM>(chunk + QH + r * 64 + 16 * swz4(r, i >> 1) + 8 * (i & 1));
+        const uint32_t M4 = 0x0F0F0F0Fu, MH = 0x30303030u;
+        u.v[0] = (w.x & M4) | ((hq.x << 4) & MH);
+        u.v[1] = (w.y & M4) | ((hq.x << 2) & MH);
+        u.v[2] = (w.z & M4) | (hq.x & MH);
+        u.v[3] = (w.w & M4) | ((hq.x >> 2) & MH);
+        u.v[4] = ((w.x >> 4) & M4) | ((hq.y << 4) & MH);
+        u.v[5] = ((w.y >> 4) & M4) | ((hq.y << 2) & MH);
+        u.v[6] = ((w.z >> 4) & M4) | (hq.y & MH);
+        u.v[7] = ((w.w >> 4) & M4) | ((hq.y >> 2) & MH);
+        uint16_t s2 = ld2(chunk + SC + r * 16 + 2 * i);
+        float d = half_bits_to_float(ld2(chunk + D + r * 2));
+        u.a[0] = __fmul_rn(d, (float)(int8_t)(s2 & 0xFF));
+        u.a[1] = __fmul_rn(d, (float)(int8_t)(s2 >> 8));
+        u.b[0] = u.b[1] = 0.0f;
+        u.off[0] = u.off[1] = 32;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Q8_0 : canonical 8 x [f16 d][i8 qs[32]]  (272 B / 256)
+// chunk: QS 128x256 B | D 128x16 B (8 x f16)
+// ------------------------------------------------------------------------------------------------
+struct FmtQ8_0 {
+    static constexpr int FAMILY = 3, SUB = 32;
+    static constexpr bool HAS_MIN = false;
+    static constexpr int QS = 0, D = 128 * 256;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 272; }
+    __host__ __device__ static constexpr int src_block_elems() { return 32; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 34; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* qs = chunk + QS + r * 256;
+        uint8_t* dd = chunk + D + r * 16;
+        for (int blk = 0; blk < 8; blk++) {
+            const uint8_t* s = src + 34 * blk;
+            bool ok = blk < nvalid;
+            dd[2 * blk] = ok ? s[0] : 0; dd[2 * blk + 1] = ok ? s[1] : 0;
+            for (int h = 0; h < 2; h++) {
+                uint8_t* dst = qs + 16 * swz8(r, 2 * blk + h);
+                for (int b = 0; b < 16; b++) dst[b] = ok ? s[2 + 16 * h + b] : 0;
+            }
+        }
+    }
+    template <bool SMEM>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w0 = ld16<SMEM>(chunk + QS + r * 256 + 16 * swz8(r, 2 * i));
+        uint4 w1 = ld16<SMEM>(chunk + QS + r * 256 + 16 * swz8(r, 2 * i + 1));
+        u.v[0] = w0.x; u.v[1] = w0.y; u.v[2] = w0.z; u.v[3] = w0.w;
+        u.v[4] = w1.x; u.v[5] = w1.y; u.v[6] = w1.z; u.v[7] = w1.w;
+        float d = half_bits_to_float(ld2(chunk + D + r * 16 + 2 * i));
+        u.a[0] = u.a[1] = d;
+        u.b[0] = u.b[1] = 0.0f;
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// G4 : AWQ / GPTQ INT4 group quantisation, W = (q - z) * s with z an integer zero point.
+// chunk: QS 128x128 B (unit order) | SC 128 x gpc x f16 | Z 128 x gpc x u8       gpc = groups per 256 k
+// ------------------------------------------------------------------------------------------------
+struct FmtG4 {
+    static constexpr int FAMILY = 4, SUB = 32;
+    static constexpr bool HAS_MIN = false;
+    static constexpr int QS = 0, SC = 128 * 128;
+    __host__ __device__ static constexpr int chunk_bytes(int gpc) { return 128 * 128 + 128 * gpc * 3; }
+    __host__ __device__ static constexpr int z_off(int gpc) { return SC + 128 * gpc * 2; }
+
+    // q[256] 4-bit values of row r in k order, sc[gpc] f16 bits, z[gpc] integer zero points
+    __device__ static void store_row(const uint8_t* q, const uint16_t* sc, const uint8_t* z, uint8_t* chunk, int r, int gpc) {
+        uint8_t* qs = chunk + QS + r * 128;
+        for (int i = 0; i < 8; i++) store_nib_unit(qs + 16 * swz8(r, i), q + 32 * i);
+        uint8_t* s = chunk + SC + r * gpc * 2;
+        uint8_t* zz = chunk + z_off(gpc) + r * gpc;
+        for (int g = 0; g < gpc; g++) { s[2 * g] = (uint8_t)(sc[g] & 0xFF); s[2 * g + 1] = (uint8_t)(sc[g] >> 8); zz[g] = z[g]; }
+    }
+    template <bool SMEM>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta meta) {
+        uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
+        u.v[0] = w.x & 0x0F0F0F0Fu; u.v[1] = w.y & 0x0F0F0F0Fu; u.v[2] = w.z & 0x0F0F0F0Fu; u.v[3] = w.w & 0x0F0F0F0Fu;
+        u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
+        u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        int gq = (i * meta.gpc) >> 3;
+        float s = half_bits_to_float(ld2(chunk + SC + (r * meta.gpc + gq) * 2));
+        int z = chunk[z_off(meta.gpc) + r * meta.gpc + gq];
+        u.a[0] = u.a[1] = s;
+        u.b[0] = u.b[1] = 0.0f;
+        u.off[0] = u.off[1] = z;
+    }
+};
+
+// signed byte e (0..31) of a unit
+__device__ __forceinline__ int unit_elem(const Unit& u, int e) { return (int)(int8_t)((u.v[e >> 2] >> (8 * (e & 3))) & 0xFF); }
+
+}  // namespace b200q

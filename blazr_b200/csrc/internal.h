@@ -1,0 +1,53 @@
+// internal.h -- host-side structures and launcher prototypes shared by the translation units of libb200q.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200q.h"
+
+struct b200q_weight {
+    int64_t N, K, N_pad, K_pad;
+    int family, source, ggml_type, group_size, sub, gpc;
+    int device;
+    int chunk_bytes;
+    int64_t T, KC;  // tiles along N, chunks along K
+    uint8_t* data;  // repacked tiles [T][KC][chunk_bytes]
+    int64_t device_bytes, canonical_bytes;
+    float* bias;    // device f32 [N] or null
+    int32_t* perm;  // device i32 [K] (GPTQ act-order) or null
+    int num_sms;
+};
+
+namespace b200q {
+
+void count_launch(int n = 1);
+
+// ---- kernels_aux.cu ----
+cudaError_t launch_repack_ggml(int family, const uint8_t* src_dev, int64_t src_row_bytes, int64_t n0, int64_t k0, const b200q_weight* w,
+                               cudaStream_t st);
+cudaError_t launch_repack_awq(const uint32_t* qweight, const float* scales, const float* zeros, int64_t N_full, int64_t n0, int64_t k0,
+                              const b200q_weight* w, int* err_flag, cudaStream_t st);
+cudaError_t launch_repack_gptq(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* perm, int zpo,
+                               int64_t N_full, int64_t n0, int64_t k0, const b200q_weight* w, int* err_flag, cudaStream_t st);
+cudaError_t launch_dequantize(const b200q_weight* w, void* out, int dtype, cudaStream_t st);
+cudaError_t launch_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t K_pad, int64_t ldx, const int32_t* perm, uint8_t* xq,
+                             cudaStream_t st);
+cudaError_t launch_act_unpack(const uint8_t* xq, int64_t M, int64_t K_pad, int8_t* q, float* d, int32_t* bsum16, cudaStream_t st);
+cudaError_t launch_int_partials(const b200q_weight* w, const uint8_t* xq, int64_t M, int32_t* out, cudaStream_t st);
+cudaError_t launch_to_bf16(const void* x, int x_dtype, int64_t M, int64_t K, int64_t K_pad, int64_t M_pad, int64_t ldx, const int32_t* perm,
+                           void* out_bf16, cudaStream_t st);
+
+// ---- matvec.cu ----
+struct MatvecPlan {
+    int grid, nstages, stage_bytes, smem_bytes, mb;
+};
+cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan);
+size_t matvec_ws_bytes(const b200q_weight* w, int64_t M);  // counters + partials (excludes the activation buffer)
+cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st);
+
+// ---- gemm_tc.cu ----
+size_t gemm_ws_bytes(const b200q_weight* w, int64_t M);
+cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, int64_t M, int64_t ldx, void* y, int y_dtype, int64_t ldy,
+                           uint8_t* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace b200q

@@ -1,0 +1,315 @@
+// kernels_aux.cu -- one-off and test-hook kernels: upload repack, dense dequantize, activation quantiser,
+// integer-partial dump, activation -> bf16 staging.
+#include "formats.cuh"
+#include "internal.h"
+
+namespace b200q {
+
+// ------------------------------------------------------------------------------------------------
+// ggml raw blocks -> tiles.  One CTA (128 threads) per chunk, thread == row.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) repack_ggml_kernel(const uint8_t* __restrict__ src, int64_t src_row_bytes, int64_t n0, int64_t k0,
+                                                           int64_t N, int64_t K, int64_t KC, uint8_t* __restrict__ dst, FmtMeta meta) {
+    int64_t kc = blockIdx.x, t = blockIdx.y;
+    int r = threadIdx.x;
+    uint8_t* chunk = dst + (t * KC + kc) * (int64_t)F::chunk_bytes(meta.gpc);
+    int64_t nl = t * TILE_ROWS + r;
+    constexpr int BE = F::src_block_elems(), BB = F::src_block_bytes();
+    int64_t kbeg = kc * CHUNK_K;
+    int nvalid = 0;
+    if (nl < N && kbeg < K) {
+        int64_t rem = (K - kbeg) / BE;
+        int per_chunk = CHUNK_K / BE;
+        nvalid = (int)(rem < per_chunk ? rem : per_chunk);
+    }
+    const uint8_t* s = src + (n0 + (nl < N ? nl : 0)) * src_row_bytes + ((k0 + kbeg) / BE) * BB;
+    F::repack_row(s, nvalid, chunk, r, meta);
+}
+
+cudaError_t launch_repack_ggml(int family, const uint8_t* src, int64_t src_row_bytes, int64_t n0, int64_t k0, const b200q_weight* w,
+                               cudaStream_t st) {
+    dim3 grid((unsigned)w->KC, (unsigned)w->T);
+    FmtMeta meta{w->gpc};
+    switch (family) {
+        case B200Q_FAM_Q4_K: repack_ggml_kernel<FmtQ4K><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta); break;
+        case B200Q_FAM_Q6_K: repack_ggml_kernel<FmtQ6K><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta); break;
+        case B200Q_FAM_Q8_0: repack_ggml_kernel<FmtQ8_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// AWQ (reference src/loader/safetensors/awq.rs:29-32,190-226): qweight u32 [K, N/8] with nibble order
+// AWQ_SHIFTS, scales f32 [K/gs, N], zeros f32 [K/gs, N] (already unpacked).
+// ------------------------------------------------------------------------------------------------
+__device__ __constant__ uint32_t kAwqShifts[8] = {0, 16, 4, 20, 8, 24, 12, 28};
+
+__global__ void __launch_bounds__(128) repack_awq_kernel(const uint32_t* __restrict__ qweight, const float* __restrict__ scales,
+                                                          const float* __restrict__ zeros, int64_t N_full, int64_t n0, int64_t k0, int64_t N,
+                                                          int64_t K, int64_t KC, int gs, int gpc, uint8_t* __restrict__ dst, int* err) {
+    int64_t kc = blockIdx.x, t = blockIdx.y;
+    int r = threadIdx.x;
+    uint8_t* chunk = dst + (t * KC + kc) * (int64_t)FmtG4::chunk_bytes(gpc);
+    int64_t nl = t * TILE_ROWS + r;
+    uint8_t q[256];
+    uint16_t sc[8];
+    uint8_t z[8];
+    for (int g = 0; g < gpc; g++) { sc[g] = 0; z[g] = 0; }
+    bool row_ok = nl < N;
+    int64_t n = n0 + (row_ok ? nl : 0);
+    int64_t n8 = N_full / 8;
+    uint32_t sh = kAwqShifts[n & 7];
+    for (int j = 0; j < 256; j++) {
+        int64_t kl = kc * CHUNK_K + j;
+        uint32_t v = 0;
+        if (row_ok && kl < K) v = (qweight[(k0 + kl) * n8 + (n >> 3)] >> sh) & 0xF;
+        q[j] = (uint8_t)v;
+    }
+    int span = CHUNK_K / gpc;  // k covered by one stored group slot
+    for (int g = 0; g < gpc; g++) {
+        int64_t kl = kc * CHUNK_K + (int64_t)g * span;
+        if (row_ok && kl < K) {
+            int64_t grp = (k0 + kl) / gs;
+            float s = scales[grp * N_full + n];
+            float zf = zeros[grp * N_full + n];
+            __half h = __float2half_rn(s);
+            if (__half2float(h) != s) atomicOr(err, 1);
+            int zi = (int)zf;
+            if ((float)zi != zf || zi < 0 || zi > 255) atomicOr(err, 2);
+            sc[g] = __half_as_ushort(h);
+            z[g] = (uint8_t)zi;
+        }
+    }
+    FmtG4::store_row(q, sc, z, chunk, r, gpc);
+}
+
+cudaError_t launch_repack_awq(const uint32_t* qweight, const float* scales, const float* zeros, int64_t N_full, int64_t n0, int64_t k0,
+                              const b200q_weight* w, int* err_flag, cudaStream_t st) {
+    dim3 grid((unsigned)w->KC, (unsigned)w->T);
+    repack_awq_kernel<<<grid, 128, 0, st>>>(qweight, scales, zeros, N_full, n0, k0, w->N, w->K, w->KC, w->group_size, w->gpc, w->data, err_flag);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GPTQ (reference src/loader/safetensors/gptq.rs:198-259): qweight u32 [K/8, N] sequential nibbles
+// along K, scales f32 [G, N], qzeros u32 [G, N/8] sequential nibbles along N, perm = group-sorting
+// permutation of K (act-order) or null.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) repack_gptq_kernel(const uint32_t* __restrict__ qweight, const float* __restrict__ scales,
+                                                           const uint32_t* __restrict__ qzeros, const int32_t* __restrict__ perm, int zpo,
+                                                           int64_t N_full, int64_t n0, int64_t k0, int64_t N, int64_t K, int64_t KC, int gs,
+                                                           int gpc, uint8_t* __restrict__ dst, int* err) {
+    int64_t kc = blockIdx.x, t = blockIdx.y;
+    int r = threadIdx.x;
+    uint8_t* chunk = dst + (t * KC + kc) * (int64_t)FmtG4::chunk_bytes(gpc);
+    int64_t nl = t * TILE_ROWS + r;
+    uint8_t q[256];
+    uint16_t sc[8];
+    uint8_t z[8];
+    for (int g = 0; g < gpc; g++) { sc[g] = 0; z[g] = 0; }
+    bool row_ok = nl < N;
+    int64_t n = n0 + (row_ok ? nl : 0);
+    for (int j = 0; j < 256; j++) {
+        int64_t kl = kc * CHUNK_K + j;
+        uint32_t v = 0;
+        if (row_ok && kl < K) {
+            int64_t kp = k0 + kl;
+            int64_t k = perm ? perm[kp] : kp;
+            v = (qweight[(k >> 3) * N_full + n] >> (4 * (k & 7))) & 0xF;
+        }
+        q[j] = (uint8_t)v;
+    }
+    int span = CHUNK_K / gpc;
+    for (int g = 0; g < gpc; g++) {
+        int64_t kl = kc * CHUNK_K + (int64_t)g * span;
+        if (row_ok && kl < K) {
+            int64_t grp = (k0 + kl) / gs;
+            float s = scales[grp * N_full + n];
+            __half h = __float2half_rn(s);
+            if (__half2float(h) != s) atomicOr(err, 1);
+            uint32_t zz = (qzeros[grp * (N_full / 8) + (n >> 3)] >> (4 * (n & 7))) & 0xF;
+            sc[g] = __half_as_ushort(h);
+            z[g] = (uint8_t)(zz + zpo);
+        }
+    }
+    FmtG4::store_row(q, sc, z, chunk, r, gpc);
+}
+
+cudaError_t launch_repack_gptq(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* perm, int zpo,
+                               int64_t N_full, int64_t n0, int64_t k0, const b200q_weight* w, int* err_flag, cudaStream_t st) {
+    dim3 grid((unsigned)w->KC, (unsigned)w->T);
+    repack_gptq_kernel<<<grid, 128, 0, st>>>(qweight, scales, qzeros, perm, zpo, N_full, n0, k0, w->N, w->K, w->KC, w->group_size, w->gpc,
+                                             w->data, err_flag);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense dequantize: out[N,K] = a * (v - off) - b  (separate multiply / subtract: bit-exact contract #1)
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) dequant_kernel(const uint8_t* __restrict__ data, int64_t N, int64_t K, int64_t KC, void* out, int dtype,
+                                                       const int32_t* __restrict__ perm, FmtMeta meta) {
+    int64_t kc = blockIdx.x, t = blockIdx.y;
+    const uint8_t* chunk = data + (t * KC + kc) * (int64_t)F::chunk_bytes(meta.gpc);
+    for (int item = threadIdx.x; item < TILE_ROWS * 8; item += blockDim.x) {
+        int r = item >> 3, i = item & 7;
+        int64_t n = t * TILE_ROWS + r;
+        if (n >= N) continue;
+        Unit u;
+        F::template load_unit<false>(chunk, r, i, u, meta);
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            int64_t kp = kc * CHUNK_K + 32 * i + e;
+            if (kp >= K) continue;
+            int h = e >> 4;
+            int q = unit_elem(u, e) - u.off[h];
+            float v = __fsub_rn(__fmul_rn(u.a[h], (float)q), u.b[h]);
+            int64_t k = perm ? perm[kp] : kp;
+            store_out(out, dtype, n * K + k, v);
+        }
+    }
+}
+
+cudaError_t launch_dequantize(const b200q_weight* w, void* out, int dtype, cudaStream_t st) {
+    dim3 grid((unsigned)w->KC, (unsigned)w->T);
+    FmtMeta meta{w->gpc};
+    switch (w->family) {
+        case B200Q_FAM_Q4_K: dequant_kernel<FmtQ4K><<<grid, 256, 0, st>>>(w->data, w->N, w->K, w->KC, out, dtype, w->perm, meta); break;
+        case B200Q_FAM_Q6_K: dequant_kernel<FmtQ6K><<<grid, 256, 0, st>>>(w->data, w->N, w->K, w->KC, out, dtype, w->perm, meta); break;
+        case B200Q_FAM_Q8_0: dequant_kernel<FmtQ8_0><<<grid, 256, 0, st>>>(w->data, w->N, w->K, w->KC, out, dtype, w->perm, meta); break;
+        case B200Q_FAM_G4: dequant_kernel<FmtG4><<<grid, 256, 0, st>>>(w->data, w->N, w->K, w->KC, out, dtype, w->perm, meta); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation quantiser: per 32-element block d = amax/127, q = roundf(x/d) (oracle orc_quantize_act).
+// Output records, chunk-major so the matvec brings one k-chunk of all M rows with one bulk copy:
+//   xq[(kc*M + m)*320] = { int8 q[256]; float d[8]; (int16 bsum16[2])[8] }
+// One CTA of 256 threads per (kc, m); warp == 32-block.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_quant_kernel(const void* __restrict__ x, int x_dtype, int64_t M, int64_t K, int64_t ldx,
+                                                         const int32_t* __restrict__ perm, uint8_t* __restrict__ xq) {
+    int64_t kc = blockIdx.x, m = blockIdx.y;
+    int t = threadIdx.x, wid = t >> 5, lane = t & 31;
+    int64_t k = kc * CHUNK_K + t;
+    float v = 0.0f;
+    if (k < K) v = load_in(x, x_dtype, m * ldx + (perm ? perm[k] : k));
+    float amax = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float d = __fdiv_rn(amax, 127.0f);
+    int q = (amax == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v, d));
+    int s = q;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);  // sum within each 16-lane half
+    int s_hi = __shfl_sync(0xffffffffu, s, 16);
+    uint8_t* rec = xq + (kc * M + m) * ACT_REC_BYTES;
+    rec[t] = (uint8_t)(int8_t)q;
+    if (lane == 0) {
+        reinterpret_cast<float*>(rec + 256)[wid] = d;
+        reinterpret_cast<uint32_t*>(rec + 288)[wid] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
+    }
+}
+
+cudaError_t launch_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t K_pad, int64_t ldx, const int32_t* perm, uint8_t* xq,
+                             cudaStream_t st) {
+    dim3 grid((unsigned)(K_pad / CHUNK_K), (unsigned)M);
+    act_quant_kernel<<<grid, 256, 0, st>>>(x, x_dtype, M, K, ldx, perm, xq);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void act_unpack_kernel(const uint8_t* __restrict__ xq, int64_t M, int64_t K_pad, int8_t* q, float* d, int32_t* bsum16) {
+    int64_t kc = blockIdx.x, m = blockIdx.y;
+    int t = threadIdx.x;
+    const uint8_t* rec = xq + (kc * M + m) * ACT_REC_BYTES;
+    q[m * K_pad + kc * CHUNK_K + t] = (int8_t)rec[t];
+    if (t < 8) {
+        d[m * (K_pad / 32) + kc * 8 + t] = reinterpret_cast<const float*>(rec + 256)[t];
+        uint32_t bs = reinterpret_cast<const uint32_t*>(rec + 288)[t];
+        bsum16[m * (K_pad / 16) + kc * 16 + 2 * t] = (int)(int16_t)(bs & 0xFFFF);
+        bsum16[m * (K_pad / 16) + kc * 16 + 2 * t + 1] = (int)(int16_t)(bs >> 16);
+    }
+}
+cudaError_t launch_act_unpack(const uint8_t* xq, int64_t M, int64_t K_pad, int8_t* q, float* d, int32_t* bsum16, cudaStream_t st) {
+    dim3 grid((unsigned)(K_pad / CHUNK_K), (unsigned)M);
+    act_unpack_kernel<<<grid, 256, 0, st>>>(xq, M, K_pad, q, d, bsum16);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer partials dump (bit-exact contract #2): out[m][n][p] = sum_{k in sub-block p} (v - off) * xq
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) int_partials_kernel(const uint8_t* __restrict__ data, const uint8_t* __restrict__ xq, int64_t N,
+                                                            int64_t M, int64_t KC, int32_t* __restrict__ out, FmtMeta meta) {
+    int64_t kc = blockIdx.x, t = blockIdx.y, m = blockIdx.z;
+    const uint8_t* chunk = data + (t * KC + kc) * (int64_t)F::chunk_bytes(meta.gpc);
+    const uint8_t* rec = xq + (kc * M + m) * ACT_REC_BYTES;
+    int64_t P = KC * (CHUNK_K / F::SUB);
+    for (int item = threadIdx.x; item < TILE_ROWS * 8; item += blockDim.x) {
+        int r = item >> 3, i = item & 7;
+        int64_t n = t * TILE_ROWS + r;
+        if (n >= N) continue;
+        Unit u;
+        F::template load_unit<false>(chunk, r, i, u, meta);
+        const int32_t* xw = reinterpret_cast<const int32_t*>(rec + 32 * i);
+        int sA = 0, sB = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { sA = __dp4a((int)u.v[k], xw[k], sA); sB = __dp4a((int)u.v[4 + k], xw[4 + k], sB); }
+        uint32_t bs = reinterpret_cast<const uint32_t*>(rec + 288)[i];
+        int bA = (int)(int16_t)(bs & 0xFFFF), bB = (int)(int16_t)(bs >> 16);
+        sA -= u.off[0] * bA;
+        sB -= u.off[1] * bB;
+        int32_t* o = out + (m * N + n) * P;
+        if (F::SUB == 32) o[kc * 8 + i] = sA + sB;
+        else { o[kc * 16 + 2 * i] = sA; o[kc * 16 + 2 * i + 1] = sB; }
+    }
+}
+
+cudaError_t launch_int_partials(const b200q_weight* w, const uint8_t* xq, int64_t M, int32_t* out, cudaStream_t st) {
+    dim3 grid((unsigned)w->KC, (unsigned)w->T, (unsigned)M);
+    FmtMeta meta{w->gpc};
+    switch (w->family) {
+        case B200Q_FAM_Q4_K: int_partials_kernel<FmtQ4K><<<grid, 256, 0, st>>>(w->data, xq, w->N, M, w->KC, out, meta); break;
+        case B200Q_FAM_Q6_K: int_partials_kernel<FmtQ6K><<<grid, 256, 0, st>>>(w->data, xq, w->N, M, w->KC, out, meta); break;
+        case B200Q_FAM_Q8_0: int_partials_kernel<FmtQ8_0><<<grid, 256, 0, st>>>(w->data, xq, w->N, M, w->KC, out, meta); break;
+        case B200Q_FAM_G4: int_partials_kernel<FmtG4><<<grid, 256, 0, st>>>(w->data, xq, w->N, M, w->KC, out, meta); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// activations -> bf16 [M_pad, K_pad] (zero padded, optional K permutation) for the tcgen05 GEMM
+// ------------------------------------------------------------------------------------------------
+__global__ void to_bf16_kernel(const void* __restrict__ x, int x_dtype, int64_t M, int64_t K, int64_t K_pad, int64_t ldx,
+                               const int32_t* __restrict__ perm, __nv_bfloat16* __restrict__ out) {
+    int64_t m = blockIdx.y;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K_pad; k += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        if (m < M && k < K) v = load_in(x, x_dtype, m * ldx + (perm ? perm[k] : k));
+        out[m * K_pad + k] = __float2bfloat16_rn(v);
+    }
+}
+cudaError_t launch_to_bf16(const void* x, int x_dtype, int64_t M, int64_t K, int64_t K_pad, int64_t M_pad, int64_t ldx, const int32_t* perm,
+                           void* out_bf16, cudaStream_t st) {
+    unsigned gx = (unsigned)((K_pad + 255) / 256);
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, (unsigned)M_pad);
+    to_bf16_kernel<<<grid, 256, 0, st>>>(x, x_dtype, M, K, K_pad, ldx, perm, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200q

@@ -1,0 +1,284 @@
+"""Python harness over the C ABI of libb200q.so (include/b200q.h).
+
+PyTorch is used only for device memory, streams and torch.distributed; every compute call goes through
+ctypes into the shared library -- the same entry points a Rust host would bind over FFI
+(INTEGRATION.md).  The interface mirrors the reference operator boundary
+(``boostr::quant::QuantMatmulOps`` / ``DequantOps`` bounds at reference src/loader/api.rs:25 and
+``DecomposedQuantTensor::new`` at src/loader/safetensors/awq.rs:218, gptq.rs:252):
+
+    client = B200Client(device)
+    w  = client.weight_from_ggml(ggml_type, raw_blocks, N, K)            # VarMap::from_gguf upload
+    w  = client.weight_from_decomposed(DecomposedQuantTensor(...))       # AWQ / GPTQ upload
+    y  = client.quant_matmul(x, w)                                       # QuantMatmulOps
+    wd = client.dequantize(w)                                            # DequantOps
+
+There is no CPU fallback: if the library is missing, fails to load, or no sm_100 GPU is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200q.so")
+
+F32, F16, BF16 = 0, 1, 2
+_TORCH2DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+PATH_AUTO, PATH_MATVEC, PATH_GEMM = 0, 1, 2
+
+
+class B200QError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200q error {code}: {msg}")
+        self.code = code
+
+
+class WeightInfo(C.Structure):
+    _fields_ = [
+        ("N", C.c_int64), ("K", C.c_int64), ("N_pad", C.c_int64), ("K_pad", C.c_int64),
+        ("family", C.c_int32), ("source", C.c_int32), ("ggml_type", C.c_int32), ("group_size", C.c_int32),
+        ("sub", C.c_int32), ("has_bias", C.c_int32), ("has_perm", C.c_int32), ("device", C.c_int32),
+        ("device_bytes", C.c_int64), ("canonical_bytes", C.c_int64), ("chunk_bytes", C.c_int32),
+    ]
+
+
+# every symbol include/b200q.h declares (tests check the library exports each one)
+EXPORTS = [
+    "b200q_version", "b200q_last_error", "b200q_device_count", "b200q_weight_from_ggml", "b200q_weight_from_ggml_shard",
+    "b200q_weight_from_awq", "b200q_weight_from_gptq", "b200q_weight_from_awq_shard", "b200q_weight_free", "b200q_weight_info",
+    "b200q_weight_set_bias", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
+    "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
+    "b200q_int_partials", "b200q_launch_count",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200q.so; fail loudly when it is missing (the product path has no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200QError(-5, f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.b200q_last_error.restype = C.c_char_p
+        L.b200q_workspace_bytes.restype = C.c_size_t
+        L.b200q_act_bytes.restype = C.c_size_t
+        L.b200q_launch_count.restype = C.c_int64
+        L.b200q_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
+        L.b200q_act_bytes.argtypes = [C.c_int64, C.c_int64]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise B200QError(rc, lib().b200q_last_error().decode())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _src(a):
+    """(pointer, on_device, keepalive) for a numpy array or torch tensor"""
+    if isinstance(a, torch.Tensor):
+        a = a.contiguous()
+        return C.c_void_p(a.data_ptr()), int(a.is_cuda), a
+    a = np.ascontiguousarray(a)
+    return C.c_void_p(a.ctypes.data), 0, a
+
+
+def shard_range(total: int, rank: int, world: int, granule: int = 1):
+    """reference src/engine/tensor_parallel.rs:61-67 (at `granule` granularity)"""
+    s, e = C.c_int64(), C.c_int64()
+    _check(lib().b200q_shard_range_blocks(C.c_int64(total), C.c_int64(granule), C.c_int64(rank), C.c_int64(world),
+                                          C.byref(s), C.byref(e)))
+    return int(s.value), int(e.value)
+
+
+@dataclass
+class DecomposedQuantMethod:
+    """mirror of boostr::quant::decomposed::DecomposedQuantMethod::{Awq, Gptq}{group_size}"""
+    kind: str  # "awq" | "gptq"
+    group_size: int
+
+
+@dataclass
+class DecomposedQuantTensor:
+    """mirror of DecomposedQuantTensor::new(qweight, scales, qzeros, g_idx, method, logical_shape)
+    (reference awq.rs:218-225, gptq.rs:252-259).  AWQ: qzeros are f32 [K/gs, N] (already unpacked);
+    GPTQ: qzeros stay packed u32 [G, N/8]."""
+    qweight: np.ndarray
+    scales: np.ndarray
+    qzeros: np.ndarray
+    g_idx: Optional[np.ndarray]
+    method: DecomposedQuantMethod
+    logical_shape: tuple
+    bias: Optional[np.ndarray] = None
+    zero_plus_one: int = 1
+
+
+class QuantWeight:
+    """Owning wrapper of an opaque b200q_weight handle (immutable once built)."""
+
+    def __init__(self, handle: C.c_void_p, device: torch.device):
+        self._h = handle
+        self.device = device
+        info = WeightInfo()
+        _check(lib().b200q_weight_info(self._h, C.byref(info)))
+        self.info = info
+        self.N, self.K = int(info.N), int(info.K)
+        self.K_pad = int(info.K_pad)
+        self.canonical_bytes = int(info.canonical_bytes)
+        self._ws = {}
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace_bytes(self, M: int) -> int:
+        return int(lib().b200q_workspace_bytes(self._h, C.c_int64(M)))
+
+    def workspace(self, M: int) -> torch.Tensor:
+        """Zero-filled scratch for calls with this M (cached per M; one in-flight call per workspace)."""
+        ws = self._ws.get(M)
+        if ws is None:
+            ws = torch.zeros(max(256, self.workspace_bytes(M)), dtype=torch.uint8, device=self.device)
+            self._ws[M] = ws
+        return ws
+
+    def free(self):
+        if self._h is not None:
+            lib().b200q_weight_free(self._h)
+            self._h = None
+            self._ws = {}
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class B200Client:
+    """The backend client: implements the QuantMatmulOps / DequantOps surface on one B200."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise B200QError(-5, "no CUDA device: the B200 path has no CPU fallback")
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.index = self.device.index or 0
+        lib()
+
+    # ---- upload -------------------------------------------------------------------------------
+    def weight_from_ggml(self, ggml_type: int, blocks, N: int, K: int, rows=None, cols=None) -> QuantWeight:
+        p, on_dev, keep = _src(blocks)
+        h = C.c_void_p()
+        n0, n1 = rows if rows is not None else (0, N)
+        k0, k1 = cols if cols is not None else (0, K)
+        with torch.cuda.device(self.device):
+            _check(lib().b200q_weight_from_ggml_shard(C.c_int32(ggml_type), p, C.c_int32(on_dev), C.c_int64(N), C.c_int64(K),
+                                                      C.c_int64(n0), C.c_int64(n1), C.c_int64(k0), C.c_int64(k1),
+                                                      C.c_int32(self.index), _stream_ptr(self.device), C.byref(h)))
+        del keep
+        return QuantWeight(h, self.device)
+
+    def weight_from_decomposed(self, t: DecomposedQuantTensor, rows=None, cols=None) -> QuantWeight:
+        N, K = t.logical_shape
+        h = C.c_void_p()
+        qw, d1, k1_ = _src(t.qweight)
+        sc, d2, k2_ = _src(np.asarray(t.scales, dtype=np.float32) if not isinstance(t.scales, torch.Tensor) else t.scales)
+        on_dev = d1
+        with torch.cuda.device(self.device):
+            if t.method.kind == "awq":
+                qz, _, k3_ = _src(np.asarray(t.qzeros, dtype=np.float32) if not isinstance(t.qzeros, torch.Tensor) else t.qzeros)
+                n0, n1 = rows if rows is not None else (0, N)
+                k0, k1 = cols if cols is not None else (0, K)
+                _check(lib().b200q_weight_from_awq_shard(qw, sc, qz, C.c_int32(on_dev), C.c_int32(t.method.group_size), C.c_int64(N),
+                                                         C.c_int64(K), C.c_int64(n0), C.c_int64(n1), C.c_int64(k0), C.c_int64(k1),
+                                                         C.c_int32(self.index), _stream_ptr(self.device), C.byref(h)))
+            elif t.method.kind == "gptq":
+                if rows is not None or cols is not None:
+                    raise B200QError(-2, "GPTQ shards are built by slicing the source tensors before upload")
+                qz, _, k3_ = _src(t.qzeros)
+                gi, _, k4_ = _src(np.asarray(t.g_idx, dtype=np.int32)) if t.g_idx is not None else (None, 0, None)
+                bi, _, k5_ = _src(np.asarray(t.bias, dtype=np.float32)) if t.bias is not None else (None, 0, None)
+                _check(lib().b200q_weight_from_gptq(qw, sc, qz, gi, bi, C.c_int32(on_dev), C.c_int32(t.method.group_size),
+                                                    C.c_int32(t.zero_plus_one), C.c_int64(N), C.c_int64(K), C.c_int32(self.index),
+                                                    _stream_ptr(self.device), C.byref(h)))
+            else:
+                raise B200QError(-2, f"unknown decomposed method {t.method.kind}")
+        return QuantWeight(h, self.device)
+
+    # ---- QuantMatmulOps ----------------------------------------------------------------------------
+    def quant_matmul(self, x: torch.Tensor, w: QuantWeight, out: Optional[torch.Tensor] = None, out_dtype=None,
+                     path: int = PATH_AUTO, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Y[..., N] = X[..., K] @ dequant(W)[N, K]^T (+bias).  x: f32 / f16 / bf16 on this device."""
+        assert x.is_cuda and x.shape[-1] == w.K, (x.shape, w.K)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, w.K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        ydt = out_dtype or x.dtype
+        if out is None:
+            out = torch.empty((M, w.N), dtype=ydt, device=x.device)
+        y2 = out.reshape(M, w.N)
+        ws = workspace if workspace is not None else w.workspace(M)
+        _check(lib().b200q_matmul_path(w.handle, C.c_int32(path), C.c_void_p(x2.data_ptr()), C.c_int32(_TORCH2DT[x2.dtype]),
+                                       C.c_int64(M), C.c_int64(x2.stride(0)), C.c_void_p(y2.data_ptr()),
+                                       C.c_int32(_TORCH2DT[y2.dtype]), C.c_int64(y2.stride(0)), C.c_void_p(ws.data_ptr()),
+                                       C.c_size_t(ws.numel()), _stream_ptr(x.device)))
+        return out.reshape(*lead, w.N)
+
+    def quantize_act(self, x: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x2 = x.reshape(-1, x.shape[-1])
+        M, K = x2.shape
+        xq = torch.empty(int(lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=x.device)
+        _check(lib().b200q_quantize_act(C.c_void_p(x2.data_ptr()), C.c_int32(_TORCH2DT[x2.dtype]), C.c_int64(M), C.c_int64(K),
+                                        C.c_int64(x2.stride(0)), C.c_void_p(perm.data_ptr()) if perm is not None else None,
+                                        C.c_void_p(xq.data_ptr()), _stream_ptr(x.device)))
+        return xq
+
+    def matmul_q8(self, xq: torch.Tensor, M: int, w: QuantWeight, out: Optional[torch.Tensor] = None, out_dtype=torch.float32,
+                  workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((M, w.N), dtype=out_dtype, device=xq.device)
+        ws = workspace if workspace is not None else w.workspace(M)
+        _check(lib().b200q_matmul_q8(w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(M), C.c_void_p(out.data_ptr()),
+                                     C.c_int32(_TORCH2DT[out.dtype]), C.c_int64(out.stride(0)), C.c_void_p(ws.data_ptr()),
+                                     C.c_size_t(ws.numel()), _stream_ptr(xq.device)))
+        return out
+
+    # ---- DequantOps --------------------------------------------------------------------------------
+    def dequantize(self, w: QuantWeight, dtype=torch.float32) -> torch.Tensor:
+        out = torch.empty((w.N, w.K), dtype=dtype, device=w.device)
+        _check(lib().b200q_dequantize(w.handle, C.c_void_p(out.data_ptr()), C.c_int32(_TORCH2DT[dtype]), _stream_ptr(w.device)))
+        return out
+
+    # ---- test hooks (bit-exact contracts) --------------------------------------------------------
+    def act_unpack(self, xq: torch.Tensor, M: int, K: int):
+        K_pad = (K + 255) // 256 * 256
+        q = torch.empty((M, K_pad), dtype=torch.int8, device=xq.device)
+        d = torch.empty((M, K_pad // 32), dtype=torch.float32, device=xq.device)
+        bs = torch.empty((M, K_pad // 16), dtype=torch.int32, device=xq.device)
+        _check(lib().b200q_act_unpack(C.c_void_p(xq.data_ptr()), C.c_int64(M), C.c_int64(K), C.c_void_p(q.data_ptr()),
+                                      C.c_void_p(d.data_ptr()), C.c_void_p(bs.data_ptr()), _stream_ptr(xq.device)))
+        return q, d, bs
+
+    def int_partials(self, w: QuantWeight, xq: torch.Tensor, M: int) -> torch.Tensor:
+        P = w.K_pad // int(w.info.sub)
+        out = torch.empty((M, w.N, P), dtype=torch.int32, device=xq.device)
+        _check(lib().b200q_int_partials(w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(M), C.c_void_p(out.data_ptr()),
+                                        _stream_ptr(xq.device)))
+        return out
+
+
+def launch_count() -> int:
+    return int(lib().b200q_launch_count())

@@ -1,0 +1,159 @@
+/*
+ * b200q.h -- C ABI of libb200q.so: the B200 (sm_100a) replacement for blazr's quantized linear-layer
+ * operator.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * What each entry point replaces in the reference (ml-rust/blazr, paths relative to /root/reference):
+ *
+ *   blazr reaches the operator only through trait bounds on the backend client
+ *   (`boostr::quant::QuantMatmulOps<R>` / `boostr::quant::DequantOps<R>`: src/loader/api.rs:25,45,67,90;
+ *   src/engine/generate_text.rs:32-33; src/engine/scheduler.rs:110-111) and through the weights its
+ *   loaders build.  The trait bodies live in the un-vendored `boostr` crate, so this ABI is shaped by the
+ *   data blazr hands over:
+ *
+ *   b200q_weight_from_ggml   <- GGUF upload: VarMap::from_gguf keeps raw ggml blocks tagged with their
+ *                               ggml type (src/loader/gguf.rs:33,38,40; type tag :365-372).
+ *   b200q_weight_from_awq    <- DecomposedQuantTensor::new(qweight u32[K,N/8], scales f32[K/gs,N],
+ *                               zeros f32[K/gs,N], None, Awq{group_size}, [N,K])
+ *                               (src/loader/safetensors/awq.rs:190-226, zeros unpack :242-263).
+ *   b200q_weight_from_gptq   <- DecomposedQuantTensor::new(qweight u32[K/8,N], scales f32[G,N],
+ *                               qzeros u32[G,N/8] packed, g_idx i32[K], Gptq{group_size}, [N,K]) + bias
+ *                               (src/loader/safetensors/gptq.rs:198-259).
+ *   b200q_matmul             <- QuantMatmulOps: Y[M,N] = X[M,K] . dequant(W)[N,K]^T (+bias) issued 7L+1
+ *                               times per forward (src/engine/executor_generate.rs:357,372; batched
+ *                               decode M = N_seq src/engine/batch_decode.rs:115-147); must be CUDA-graph
+ *                               capturable (src/engine/cuda_graphs.rs:101-130).
+ *   b200q_dequantize         <- DequantOps: packed blocks -> dense tensor (src/loader/gguf.rs:25,53,77).
+ *   b200q_shard_range /
+ *   b200q_weight_*_shard     <- TensorParallelState::shard_range (src/engine/tensor_parallel.rs:61-67),
+ *                               load_model_tp (src/loader/api.rs:39-56).
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative b200q_status; it never throws or aborts.
+ *     b200q_last_error() returns a thread-local message for the last failure on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Weight handles are immutable after creation: share them freely across threads and streams.
+ *   - Compute entry points do no allocation, no host synchronisation and read no host scalars after
+ *     launch, so they may be captured into CUDA graphs.  Scratch comes from the caller's `workspace`
+ *     (>= b200q_workspace_bytes(w, M) bytes, 256-byte aligned, ZERO-FILLED before its first use; one
+ *     workspace must not be used by two in-flight calls at once).
+ *   - There is NO CPU fallback: an unsupported format/shape is an error code.
+ */
+#ifndef B200Q_H
+#define B200Q_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200q_status {
+    B200Q_OK = 0,
+    B200Q_ERR_INVALID_ARG = -1,
+    B200Q_ERR_UNSUPPORTED = -2,
+    B200Q_ERR_CUDA = -3,
+    B200Q_ERR_WORKSPACE = -4,
+    B200Q_ERR_NO_DEVICE = -5
+} b200q_status;
+
+typedef enum b200q_dtype { B200Q_F32 = 0, B200Q_F16 = 1, B200Q_BF16 = 2 } b200q_dtype;
+
+/* internal format families, reported by b200q_weight_info */
+typedef enum b200q_family {
+    B200Q_FAM_Q4_K = 1, B200Q_FAM_Q6_K = 2, B200Q_FAM_Q8_0 = 3, B200Q_FAM_G4 = 4 /* AWQ/GPTQ */,
+    B200Q_FAM_Q5_K = 5, B200Q_FAM_Q4_0 = 6, B200Q_FAM_Q4_1 = 7, B200Q_FAM_Q5_0 = 8, B200Q_FAM_Q5_1 = 9,
+    B200Q_FAM_Q2_K = 10, B200Q_FAM_Q3_K = 11, B200Q_FAM_IQ4_NL = 12, B200Q_FAM_IQ4_XS = 13
+} b200q_family;
+
+/* source kinds */
+#define B200Q_SRC_GGML 0
+#define B200Q_SRC_AWQ 1
+#define B200Q_SRC_GPTQ 2
+
+typedef struct b200q_weight b200q_weight; /* opaque */
+
+typedef struct b200q_weight_info_t {
+    int64_t N, K;          /* logical [out_features, in_features] */
+    int64_t N_pad, K_pad;  /* padded to the 128 x 256 tile grid */
+    int32_t family;        /* b200q_family */
+    int32_t source;        /* B200Q_SRC_* */
+    int32_t ggml_type;     /* ggml type id for GGML sources, else -1 */
+    int32_t group_size;    /* AWQ/GPTQ group size, else 0 */
+    int32_t sub;           /* width of the integer-partial sub-block: 16 or 32 */
+    int32_t has_bias, has_perm;
+    int32_t device;
+    int64_t device_bytes;    /* bytes of the repacked device buffer */
+    int64_t canonical_bytes; /* bytes of the canonical (on-disk) packed weight: the roofline's algorithmic bytes */
+    int32_t chunk_bytes;     /* bytes of one 128-row x 256-k tile */
+} b200q_weight_info_t;
+
+int32_t b200q_version(void);
+const char* b200q_last_error(void);
+int32_t b200q_device_count(void);
+
+/* ---- weight upload (one-off; synchronises `stream` before returning; host source may be freed) ---- */
+/* host_blocks: N rows of K/block ggml blocks, row-major, exactly as stored in a GGUF file.
+ * src_on_device != 0 means `blocks` is already a device pointer on `device`. */
+int32_t b200q_weight_from_ggml(int32_t ggml_type, const void* blocks, int32_t src_on_device, int64_t N, int64_t K,
+                               int32_t device, void* stream, b200q_weight** out);
+/* Same, keeping only rows [n0,n1) and columns [k0,k1) of the logical [N,K] weight (TP sharding at block
+ * granularity: k0,k1 must be multiples of the ggml block size). */
+int32_t b200q_weight_from_ggml_shard(int32_t ggml_type, const void* blocks, int32_t src_on_device, int64_t N, int64_t K,
+                                     int64_t n0, int64_t n1, int64_t k0, int64_t k1, int32_t device, void* stream,
+                                     b200q_weight** out);
+/* AWQ triplet as blazr's loader builds it.  Scales must be f16-representable, zeros integers in [0,15]. */
+int32_t b200q_weight_from_awq(const uint32_t* qweight, const float* scales, const float* zeros, int32_t src_on_device,
+                              int32_t group_size, int64_t N, int64_t K, int32_t device, void* stream, b200q_weight** out);
+/* GPTQ group as blazr's loader builds it.  g_idx and bias may be NULL.  zero_plus_one selects the
+ * AutoGPTQ-v1 convention (stored zero = z-1); blazr does not reveal which one boostr uses. */
+int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* g_idx,
+                               const float* bias, int32_t src_on_device, int32_t group_size, int32_t zero_plus_one,
+                               int64_t N, int64_t K, int32_t device, void* stream, b200q_weight** out);
+/* TP shards of the INT4 layouts: rows [n0,n1) (multiple of 8) and columns [k0,k1) (multiple of group_size;
+ * GPTQ act-order weights cannot be split along K). */
+int32_t b200q_weight_from_awq_shard(const uint32_t* qweight, const float* scales, const float* zeros, int32_t src_on_device,
+                                    int32_t group_size, int64_t N, int64_t K, int64_t n0, int64_t n1, int64_t k0, int64_t k1,
+                                    int32_t device, void* stream, b200q_weight** out);
+int32_t b200q_weight_free(b200q_weight* w);
+int32_t b200q_weight_info(const b200q_weight* w, b200q_weight_info_t* info);
+/* optional f32 bias [N] (device copy is made) added in every matmul epilogue */
+int32_t b200q_weight_set_bias(b200q_weight* w, const float* bias, int32_t src_on_device, void* stream);
+
+/* reference src/engine/tensor_parallel.rs:61-67 */
+int32_t b200q_shard_range(int64_t total, int64_t rank, int64_t world, int64_t* start, int64_t* end);
+/* shard_range applied at `granule` granularity (rows of 1 / blocks of 32,128,256 ...) */
+int32_t b200q_shard_range_blocks(int64_t total, int64_t granule, int64_t rank, int64_t world, int64_t* start, int64_t* end);
+
+/* ---- compute ---- */
+size_t b200q_workspace_bytes(const b200q_weight* w, int64_t M);
+/* Y[M,N] (ldy elements between rows) = X[M,K] (ldx) . dequant(W)^T (+bias).  x,y,workspace: device memory.
+ * M == 1..4 : dp4a stream-K matvec on int8-quantised activations (decode);
+ * M >= 5    : tcgen05/TMEM dequant-GEMM on bf16 activations (batched decode and prefill). */
+int32_t b200q_matmul(const b200q_weight* w, const void* x, int32_t x_dtype, int64_t M, int64_t ldx, void* y, int32_t y_dtype,
+                     int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+/* Split form for callers that share one quantised activation among several weights (q,k,v / gate,up):
+ * quantise once into `xq` (b200q_act_bytes(K, M) bytes), then b200q_matmul_q8 for each weight (M <= 4). */
+size_t b200q_act_bytes(int64_t K, int64_t M);
+int32_t b200q_quantize_act(const void* x, int32_t x_dtype, int64_t M, int64_t K, int64_t ldx, const int32_t* perm /*nullable, device*/,
+                           void* xq, void* stream);
+int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* y, int32_t y_dtype, int64_t ldy,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* Force a path (testing / benchmarking): 0 = auto, 1 = dp4a matvec, 2 = tcgen05 GEMM */
+int32_t b200q_matmul_path(const b200q_weight* w, int32_t path, const void* x, int32_t x_dtype, int64_t M, int64_t ldx, void* y,
+                          int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dense dequantisation: out[N,K] row-major in `dtype` (f32 is bit-exact: a*q - b, no FMA) */
+int32_t b200q_dequantize(const b200q_weight* w, void* out, int32_t dtype, void* stream);
+/* test hooks for the bit-exact contracts: activation quantiser planes and integer dot partials.
+ * q int8[M,K_pad], d f32[M,K_pad/32], bsum16 i32[M,K_pad/16]; partials i32[M,N,K_pad/sub]. */
+int32_t b200q_act_unpack(const void* xq, int64_t M, int64_t K, int8_t* q, float* d, int32_t* bsum16, void* stream);
+int32_t b200q_int_partials(const b200q_weight* w, const void* xq, int64_t M, int32_t* partials, void* stream);
+
+/* number of kernels the library has launched on this process (all threads); for bench accounting */
+int64_t b200q_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H */
