@@ -407,4 +407,10 @@ int32_t b200q_int_partials(const b200q_weight* w, const void* xq, int64_t M, int
     return B200Q_OK;
 }
 
+/* debug only (not in b200q.h): per-CTA globaltimer trace of the matvec kernel */
+int32_t b200q_debug_set_matvec_trace(void* dev_buf) {
+    set_matvec_trace((long long*)dev_buf);
+    return B200Q_OK;
+}
+
 }  // extern "C"

@@ -62,6 +62,12 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
         : "memory");
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---- programmatic dependent launch ----
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -1,8 +1,362 @@
-// gemm_tc.cu -- placeholder until the tcgen05 dequant-GEMM lands (returns "not supported": no fallback).
+// gemm_tc.cu -- dequant-GEMM on the 5th-generation tensor cores (tcgen05 + TMEM) for M >= 5:
+// batched decode (HBM-bound) and prefill (tensor-bound) through one kernel.
+//
+// Design (DESIGN.md "Kernel 2"): Y^T tile = W_tile[128 n x K] . X_tile[Mt m x K]^T
+//   * UMMA M = 128 weight rows, UMMA N = Mt <= 256 activation rows, K = 16 per instruction, f16 x f16 -> f32;
+//   * the weight operand never touches shared memory as f16: packed chunks arrive by cp.async.bulk (TMA
+//     engine), 8 dequant warps (thread == weight row, bank-conflict-free thanks to the upload swizzle) expand
+//     them in registers and write f16 pairs straight into TENSOR MEMORY with tcgen05.st; the MMA reads A
+//     from TMEM (the ".ts" form), so shared-memory bandwidth is spent only on the 4.5-8.5 bit packed bytes
+//     and on the activation tile;
+//   * the activation tile comes from a pre-staged f16 copy laid out as 128B-swizzled K-major UMMA tiles, one
+//     contiguous cp.async.bulk per 64-k sub-stage (no tensor map needed);
+//   * accumulators (128 lanes x Mt columns f32) live in TMEM; 8 TMEM A-slots of 64 k form the
+//     dequant -> MMA ring; tcgen05.commit releases A-slots / X stages and publishes the accumulator;
+//   * warp roles: 0 = weight-chunk producer, 2 = activation producer, 1 = TMEM allocator + single-thread
+//     MMA issuer, 4..11 = dequant + epilogue (tcgen05.ld -> bias -> global).
+#include "formats.cuh"
 #include "internal.h"
+
 namespace b200q {
-size_t gemm_ws_bytes(const b200q_weight*, int64_t) { return 0; }
-cudaError_t launch_gemm_tc(const b200q_weight*, const void*, int, int64_t, int64_t, void*, int, int64_t, uint8_t*, size_t, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+constexpr int GT_THREADS = 384;
+constexpr int GT_NX = 4;       // activation sub-stage ring (64 k each)
+constexpr int GT_ASLOTS = 8;   // TMEM A slots (32 columns = 64 k of f16 each)
+constexpr int GT_MAX_NW = 4;   // weight chunk ring
+constexpr int GT_D_COL = 0;    // accumulator columns [0, 256)
+constexpr int GT_A_COL = 256;  // A slots in columns [256, 512)
+constexpr int GT_HDR = 1024;
+
+struct GemmParams {
+    const uint8_t* w;
+    const uint8_t* xs;
+    void* y;
+    const float* bias;
+    int64_t N, M, ldy;
+    int y_dtype;
+    int T, KC, MT, Mt;
+    int gpc, chunk_bytes, nw, w_stage_bytes, x_stage_bytes;
+    uint32_t idesc;
+};
+
+// ---- tcgen05 wrappers ----
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+    d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float small_int_to_float(int q) { return __int_as_float(0x4B400000 + q) - 12582912.0f; }
+
+// 32 weights of a unit -> 16 packed f16 pairs in k order:  w = a*(v-off) - b
+__device__ __forceinline__ void unit_to_f16(const Unit& u, uint32_t* out) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int h = k >> 2;
+        const uint32_t wv = u.v[k];
+        float f[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int q = (int)(int8_t)((wv >> (8 * c)) & 0xFFu) - u.off[h];
+            f[c] = fmaf(u.a[h], small_int_to_float(q), -u.b[h]);
+        }
+        __half2 p0 = __floats2half2_rn(f[0], f[1]);
+        __half2 p1 = __floats2half2_rn(f[2], f[3]);
+        out[2 * k] = *reinterpret_cast<uint32_t*>(&p0);
+        out[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p1);
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_w = full_w + GT_MAX_NW;
+    uint64_t* full_x = empty_w + GT_MAX_NW;
+    uint64_t* empty_x = full_x + GT_NX;
+    uint64_t* a_full = empty_x + GT_NX;
+    uint64_t* a_empty = a_full + GT_ASLOTS;
+    uint64_t* d_full = a_empty + GT_ASLOTS;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_full + 1);
+    uint8_t* xst = smem + GT_HDR;
+    uint8_t* wst = xst + (size_t)GT_NX * p.x_stage_bytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < p.nw; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 8); }
+        for (int s = 0; s < GT_NX; s++) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+        for (int s = 0; s < GT_ASLOTS; s++) { mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
+        mbar_init(d_full, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    const int total_tiles = p.T * p.MT;
+    const int KS = p.KC * 4;  // 64-k sub-stages along K
+
+    if (warp == 0) {
+        // ===================== weight chunk producer =====================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int s = 0;
+            uint32_t ph = 1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int t = tile / p.MT;
+                const uint8_t* src = p.w + (size_t)t * p.KC * p.chunk_bytes;
+                for (int kc = 0; kc < p.KC; kc++) {
+                    mbar_wait(&empty_w[s], ph);
+                    mbar_arrive_expect_tx(&full_w[s], (uint32_t)p.chunk_bytes);
+                    if (p.MT == 1) bulk_g2s_hint(wst + (size_t)s * p.w_stage_bytes, src, (uint32_t)p.chunk_bytes, &full_w[s], pol);
+                    else bulk_g2s(wst + (size_t)s * p.w_stage_bytes, src, (uint32_t)p.chunk_bytes, &full_w[s]);
+                    src += p.chunk_bytes;
+                    if (++s == p.nw) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== activation tile producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile % p.MT;
+                const uint8_t* src = p.xs + (size_t)mt * KS * p.x_stage_bytes;
+                for (int ks = 0; ks < KS; ks++) {
+                    mbar_wait(&empty_x[s], ph);
+                    mbar_arrive_expect_tx(&full_x[s], (uint32_t)p.x_stage_bytes);
+                    bulk_g2s(xst + (size_t)s * p.x_stage_bytes, src, (uint32_t)p.x_stage_bytes, &full_x[s]);
+                    src += p.x_stage_bytes;
+                    if (++s == GT_NX) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== single-thread MMA issuer =====================
+        if (lane == 0) {
+            int xs = 0, as = 0;
+            uint32_t xph = 0, aph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int ks = 0; ks < KS; ks++) {
+                    mbar_wait(&a_full[as], aph);
+                    mbar_wait(&full_x[xs], xph);
+                    tc_fence_after();
+                    const uint32_t a_addr = tmem + GT_A_COL + as * 32;
+                    const uint64_t bdesc = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        tc_mma_ts(tmem + GT_D_COL, a_addr + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, (ks | kk) != 0 ? 1u : 0u);
+                    tc_commit(&a_empty[as]);
+                    tc_commit(&empty_x[xs]);
+                    if (++xs == GT_NX) { xs = 0; xph ^= 1u; }
+                    if (++as == GT_ASLOTS) { as = 0; aph ^= 1u; }
+                }
+                tc_commit(d_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== dequant (thread == weight row) + epilogue =====================
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
+        const FmtMeta meta{p.gpc};
+        int ws = 0, as = 0;
+        uint32_t wph = 0, aph = 1, dph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int t = tile / p.MT, mt = tile % p.MT;
+            for (int kc = 0; kc < p.KC; kc++) {
+                mbar_wait(&full_w[ws], wph);
+                const uint8_t* wc = wst + (size_t)ws * p.w_stage_bytes;
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    Unit u;
+                    F::template load_unit<true>(wc, r, 2 * j + h, u, meta);
+                    uint32_t pk[16];
+                    unit_to_f16(u, pk);
+                    mbar_wait(&a_empty[as], aph);
+                    tc_fence_after();
+                    tc_st16(lane_base + GT_A_COL + as * 32 + 16 * h, pk);
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[as]);
+                    if (++as == GT_ASLOTS) { as = 0; aph ^= 1u; }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_w[ws]);
+                if (++ws == p.nw) { ws = 0; wph ^= 1u; }
+            }
+            // ---- epilogue: accumulator rows = n, columns = m ----
+            mbar_wait(d_full, dph);
+            dph ^= 1u;
+            tc_fence_after();
+            const int64_t n = (int64_t)t * TILE_ROWS + r;
+            const float bv = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
+            const int half_cols = p.Mt >> 1;
+            for (int cb = 0; cb < half_cols; cb += 16) {
+                uint32_t v[16];
+                tc_ld16(lane_base + GT_D_COL + h * half_cols + cb, v);
+                tc_wait_ld();
+                if (n < p.N) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) {
+                        const int64_t m = (int64_t)mt * p.Mt + h * half_cols + cb + c;
+                        if (m < p.M) store_out(p.y, p.y_dtype, m * p.ldy + n, __uint_as_float(v[c]) + bv);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation staging: x[M,K] (f32/f16/bf16) -> f16 UMMA tiles  xs[mt][ks][Mt rows x 128 B, SW128]
+// ------------------------------------------------------------------------------------------------
+__global__ void stage_x_kernel(const void* __restrict__ x, int x_dtype, int64_t M, int64_t K, int64_t ldx, const int32_t* __restrict__ perm,
+                               int Mt, int KS, uint8_t* __restrict__ xs) {
+    const int ks = blockIdx.x;
+    const int64_t m = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;  // row in padded space
+    const int kk = threadIdx.x;                                          // 0..63
+    const int64_t mt = m / Mt;
+    const int mr = (int)(m % Mt);
+    const int64_t k = (int64_t)ks * 64 + kk;
+    float v = 0.0f;
+    if (m < M && k < K) v = load_in(x, x_dtype, m * ldx + (perm ? perm[k] : k));
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    uint8_t* dst = xs + ((size_t)(mt * KS + ks) * Mt) * 128 + (size_t)mr * 128 + ((((kk >> 3) ^ (mr & 7)) << 4) + ((kk & 7) << 1));
+    *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+}
+
+static int pick_mt(int64_t M, int* MT) {
+    int64_t mtiles = (M + 255) / 256;
+    int64_t per = (M + mtiles - 1) / mtiles;
+    int Mt = (int)((per + 31) / 32 * 32);
+    *MT = (int)mtiles;
+    return Mt;
+}
+
+size_t gemm_ws_bytes(const b200q_weight* w, int64_t M) {
+    if (M < 1) return 0;
+    int MT;
+    int Mt = pick_mt(M, &MT);
+    return (size_t)MT * Mt * (size_t)w->K_pad * 2;
+}
+
+template <class F>
+static cudaError_t launch_gemm_t(const GemmParams& p, int grid, int smem, cudaStream_t st) {
+    static bool configured[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    gemm_tc_kernel<F><<<grid, GT_THREADS, smem, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, int64_t M, int64_t ldx, void* y, int y_dtype, int64_t ldy,
+                           uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws_bytes;
+    int MT;
+    const int Mt = pick_mt(M, &MT);
+    const int KS = (int)w->KC * 4;
+    // 1. stage activations as f16 UMMA tiles
+    {
+        dim3 block(64, 4);
+        dim3 grid((unsigned)KS, (unsigned)((int64_t)MT * Mt / 4));
+        stage_x_kernel<<<grid, block, 0, st>>>(x, x_dtype, M, w->K, ldx, w->perm, Mt, KS, ws);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    // 2. GEMM
+    GemmParams p;
+    p.w = w->data;
+    p.xs = ws;
+    p.y = y;
+    p.bias = w->bias;
+    p.N = w->N;
+    p.M = M;
+    p.ldy = ldy;
+    p.y_dtype = y_dtype;
+    p.T = (int)w->T;
+    p.KC = (int)w->KC;
+    p.MT = MT;
+    p.Mt = Mt;
+    p.gpc = w->gpc;
+    p.chunk_bytes = w->chunk_bytes;
+    p.w_stage_bytes = (w->chunk_bytes + 127) & ~127;
+    p.x_stage_bytes = Mt * 128;
+    int avail = 227 * 1024 - GT_HDR - GT_NX * p.x_stage_bytes;
+    int nw = avail / p.w_stage_bytes;
+    if (nw > GT_MAX_NW) nw = GT_MAX_NW;
+    if (nw < 2) return cudaErrorNotSupported;
+    p.nw = nw;
+    p.idesc = (1u << 4) | ((uint32_t)(Mt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major A/B, M=128, N=Mt
+    int smem = GT_HDR + GT_NX * p.x_stage_bytes + nw * p.w_stage_bytes;
+    int64_t tiles = (int64_t)p.T * MT;
+    int grid = (int)(tiles < w->num_sms ? tiles : w->num_sms);
+    switch (w->family) {
+        case B200Q_FAM_Q4_K: return launch_gemm_t<FmtQ4K>(p, grid, smem, st);
+        case B200Q_FAM_Q6_K: return launch_gemm_t<FmtQ6K>(p, grid, smem, st);
+        case B200Q_FAM_Q8_0: return launch_gemm_t<FmtQ8_0>(p, grid, smem, st);
+        case B200Q_FAM_G4: return launch_gemm_t<FmtG4>(p, grid, smem, st);
+        default: return cudaErrorNotSupported;
+    }
+}
+
 }  // namespace b200q

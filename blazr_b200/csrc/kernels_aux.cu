@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(256) act_quant_kernel(const void* __restrict__
     int64_t kc = blockIdx.x, m = blockIdx.y;
     int t = threadIdx.x, wid = t >> 5, lane = t & 31;
     int64_t k = kc * CHUNK_K + t;
+    pdl_launch_dependents();  // the matvec that consumes xq may start prefetching its weights now
+    pdl_wait();               // x is produced by the preceding kernel; xq may still be read by an earlier matvec
     float v = 0.0f;
     if (k < K) v = load_in(x, x_dtype, m * ldx + (perm ? perm[k] : k));
     float amax = fabsf(v);
@@ -221,10 +223,18 @@ __global__ void __launch_bounds__(256) act_quant_kernel(const void* __restrict__
 
 cudaError_t launch_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t K_pad, int64_t ldx, const int32_t* perm, uint8_t* xq,
                              cudaStream_t st) {
-    dim3 grid((unsigned)(K_pad / CHUNK_K), (unsigned)M);
-    act_quant_kernel<<<grid, 256, 0, st>>>(x, x_dtype, M, K, ldx, perm, xq);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(K_pad / CHUNK_K), (unsigned)M);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, act_quant_kernel, x, x_dtype, M, K, ldx, perm, xq);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 __global__ void act_unpack_kernel(const uint8_t* __restrict__ xq, int64_t M, int64_t K_pad, int8_t* q, float* d, int32_t* bsum16) {

@@ -6,20 +6,24 @@
 //   * one producer thread feeds a ring of shared-memory stages with cp.async.bulk (TMA engine, 1-D,
 //     mbarrier complete_tx): 1 copy of the 18-35 KB weight chunk + 1 copy of the M x 320 B quantised
 //     activation record per stage, so ~100 KB per SM are in flight independent of occupancy;
-//   * 8 consumer warps: warp w owns rows 16w..16w+15 of the tile, 8 lanes x 16 B walk one row's
+//   * 16 consumer warps: warp w owns rows 8w..8w+7 of the tile, 8 lanes x 16 B walk one row's
 //     256-k chunk (unit i = 32 consecutive k), 4 rows per step; activations stay in registers for the
-//     16 rows; integer dot products with dp4a, per-sub-block scales applied in f32;
+//     8 rows; integer dot products with dp4a, per-sub-block scales applied in f32;
 //   * at tile end an 8-lane shuffle reduction; tiles split between CTAs are combined DETERMINISTICALLY
 //     through per-CTA partial slots in the workspace: the last CTA to arrive (atomic counter) sums the
 //     partials in CTA order and writes y (no float atomics, no inter-CTA waiting).
+#include <cstdlib>
+
 #include "formats.cuh"
 #include "internal.h"
 
 namespace b200q {
 
-constexpr int MV_CONSUMER_WARPS = 8;
-constexpr int MV_THREADS = (MV_CONSUMER_WARPS + 1) * 32;
-constexpr int MV_MAX_STAGES = 8;
+constexpr int MV_CONSUMER_WARPS = 16;
+constexpr int MV_THREADS = (MV_CONSUMER_WARPS + 2) * 32;  // + producer warp + fix-up warp
+constexpr int MV_ROWS_PER_WARP = TILE_ROWS / MV_CONSUMER_WARPS;  // 8
+constexpr int MV_STEPS = MV_ROWS_PER_WARP / 4;                    // 2 (4 rows per step, 8 lanes per row)
+constexpr int MV_MAX_STAGES = 10;
 constexpr int MV_HDR_BYTES = 256;  // barriers + flags
 
 struct MatvecParams {
@@ -34,25 +38,58 @@ struct MatvecParams {
     int64_t ldy;
     int64_t KC, C;
     int gpc, nstages, chunk_bytes, stage_bytes;
+    long long* trace;  // debug: 4 x globaltimer per CTA (null in production)
+    int debug_flags;   // debug: bit0 = consumers skip the math (measures the pure TMA stream)
+    int l2_prefetch_chunks;  // per CTA: chunks beyond the smem ring to pull into L2 before griddepcontrol.wait
 };
 
 __device__ __forceinline__ int64_t sk_begin(int64_t g, int64_t C, int64_t G) { return g * C / G; }
 __device__ __forceinline__ int64_t sk_owner(int64_t c, int64_t C, int64_t G) { return ((c + 1) * G - 1) / C; }
 
+// Processing order of a CTA's chunk range [c0,c1): the two tiles it shares with its neighbours first
+// (head = tail end of tile t_first, then tail = first chunks of tile t_last), the tiles it owns entirely last.
+// Both contributors of a split tile therefore finish their share early in their lifetime and the
+// fix-up (atomic arrival + ordered reduction by the last arriver) happens mid-stream instead of in the tail.
+struct SkPlan {
+    int nH, nT, nF;          // chunks in the head / tail / full segments
+    int kcH;                 // k-chunk index at which the head segment starts (tail and full start at 0)
+    int tH, tT, tF;          // tile indices: head tile, tail tile, first full tile
+};
+__device__ __forceinline__ SkPlan sk_plan(int64_t c0, int64_t c1, int64_t KC) {
+    SkPlan s;
+    const int64_t t0 = c0 / KC, t1 = (c1 - 1) / KC;
+    const int kc0 = (int)(c0 - t0 * KC);
+    const int64_t head_end = (kc0 != 0 || c1 < (t0 + 1) * KC) ? ((t0 + 1) * KC < c1 ? (t0 + 1) * KC : c1) : c0;
+    s.nH = (int)(head_end - c0);
+    s.kcH = kc0;
+    s.tH = (int)t0;
+    int64_t tail_begin = c1;
+    if (c1 > head_end && c1 != (t1 + 1) * KC) tail_begin = t1 * KC > head_end ? t1 * KC : head_end;
+    s.nT = (int)(c1 - tail_begin);
+    s.tT = (int)t1;
+    s.nF = (int)(tail_begin - head_end);
+    s.tF = (int)(head_end / KC);
+    return s;
+}
+
 template <class F, int MB>
-__global__ void __launch_bounds__(MV_THREADS, (MB <= 2 ? 2 : 1)) matvec_kernel(const MatvecParams p) {
+__global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + MV_MAX_STAGES;
-    volatile int* sflag = reinterpret_cast<volatile int*>(smem + 2 * MV_MAX_STAGES * 8);
     uint8_t* stages = smem + MV_HDR_BYTES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t G = gridDim.x, g = blockIdx.x;
+    if (p.trace && tid == 0) p.trace[g * 8 + 0] = globaltimer_ns();
     const int64_t c0 = sk_begin(g, p.C, G), c1 = sk_begin(g + 1, p.C, G);
+    const int n_chunks = (int)(c1 - c0);
+    const int KC = (int)p.KC;
     const int nst = p.nstages;
+    SkPlan& sp = *reinterpret_cast<SkPlan*>(smem + 2 * MV_MAX_STAGES * 8);       // shared plan (computed once)
 
     if (tid == 0) {
+        sp = sk_plan(c0, c1, p.KC);
         for (int s = 0; s < nst; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], MV_CONSUMER_WARPS);
@@ -60,41 +97,130 @@ __global__ void __launch_bounds__(MV_THREADS, (MB <= 2 ? 2 : 1)) matvec_kernel(c
         fence_mbar_init();
         fence_proxy_async();
     }
+    pdl_launch_dependents();  // let the next kernel of the stream start its own weight prefetch
     __syncthreads();
 
     if (warp == MV_CONSUMER_WARPS) {
-        // ===================== producer =====================
+        // ===================== producer: one thread drives the TMA engine =====================
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
             const uint32_t xbytes = (uint32_t)p.M * ACT_REC_BYTES;
-            int64_t it = 0;
-            for (int64_t c = c0; c < c1; c++, it++) {
-                int s = (int)(it % nst);
-                uint32_t round = (uint32_t)(it / nst);
-                mbar_wait(&empty[s], (round & 1u) ^ 1u);
-                uint8_t* st = stages + (size_t)s * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)p.chunk_bytes + xbytes);
-                bulk_g2s_hint(st, p.w + c * (int64_t)p.chunk_bytes, (uint32_t)p.chunk_bytes, &full[s], pol);
-                bulk_g2s(st + p.chunk_bytes, p.xq + (c % p.KC) * (int64_t)xbytes, xbytes, &full[s]);
+            const uint32_t wbytes = (uint32_t)p.chunk_bytes;
+            // j-th processed chunk -> (weight address, k-chunk index)
+            const uint8_t* base = p.w + c0 * (int64_t)wbytes;
+            auto chunk_src = [&](int j) -> const uint8_t* {
+                if (j < sp.nH) return base + (size_t)j * wbytes;
+                if (j < sp.nH + sp.nT) return base + (size_t)(sp.nH + sp.nF + (j - sp.nH)) * wbytes;
+                return base + (size_t)(sp.nH + (j - sp.nH - sp.nT)) * wbytes;
+            };
+            auto chunk_kc = [&](int j) -> int {
+                if (j < sp.nH) return sp.kcH + j;
+                if (j < sp.nH + sp.nT) return j - sp.nH;
+                return (j - sp.nH - sp.nT) % KC;
+            };
+            // Phase 1 (before griddepcontrol.wait): weights do not depend on the preceding kernels.  Fill the
+            // shared-memory ring and ask the TMA engine to pull the rest of this CTA's range into L2, so HBM
+            // keeps streaming across the kernel boundary while the predecessor drains.
+            const int pre = n_chunks < nst ? n_chunks : nst;
+            for (int j = 0; j < pre; j++) {
+                mbar_arrive_expect_tx(&full[j], wbytes + xbytes);
+                bulk_g2s_hint(stages + (size_t)j * p.stage_bytes, chunk_src(j), wbytes, &full[j], pol);
             }
+            int npf = n_chunks - pre;
+            if (npf > p.l2_prefetch_chunks) npf = p.l2_prefetch_chunks;
+            for (int j = pre; j < pre + npf; j++)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(chunk_src(j)), "r"(wbytes) : "memory");
+            pdl_wait();  // activations (written by the preceding kernel) are visible from here on
+            if (p.trace) p.trace[g * 8 + 4] = globaltimer_ns();
+            for (int j = 0; j < pre; j++)
+                bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[j]);
+            int s = 0;
+            uint32_t ph = 0;  // second use of each stage waits for the consumers' first release (phase 0)
+            for (int j = pre; j < n_chunks; j++) {
+                mbar_wait(&empty[s], ph);
+                uint8_t* st = stages + (size_t)s * p.stage_bytes;
+                mbar_arrive_expect_tx(&full[s], wbytes + xbytes);
+                bulk_g2s_hint(st, chunk_src(j), wbytes, &full[s], pol);
+                bulk_g2s(st + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[s]);
+                if (++s == nst) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    if (warp == MV_CONSUMER_WARPS + 1) {
+        // ===================== fix-up warp: arrival atomics + ordered reduction of split tiles =====================
+        // Runs beside the consumers (they only bar.arrive), so neither the math nor the TMA stream ever waits
+        // for an atomic round trip.  Split tiles are processed first, so this finishes long before the CTA does.
+        if (sp.nH == 0 && sp.nT == 0) return;
+        pdl_wait();
+        // arrival bookkeeping is computed before the barriers: only the atomic round trip is on the critical path
+        int64_t tqs[2] = {sp.tH, sp.tT};
+        int gfs[2], ncs[2], sgfs[2];
+#pragma unroll
+        for (int seg = 0; seg < 2; seg++) {
+            const int64_t gf = sk_owner(tqs[seg] * p.KC, p.C, G), gl = sk_owner((tqs[seg] + 1) * p.KC - 1, p.C, G);
+            gfs[seg] = (int)gf;
+            ncs[seg] = (int)(gl - gf + 1);
+            sgfs[seg] = (sk_begin(gf, p.C, G) == tqs[seg] * p.KC) ? 0 : 1;  // later contributors start inside the tile: slot 0
+        }
+#pragma unroll
+        for (int seg = 0; seg < 2; seg++) {
+            if ((seg == 0 ? sp.nH : sp.nT) == 0) continue;
+            const int64_t tq = tqs[seg];
+            const int gf = gfs[seg], gl = gfs[seg] + ncs[seg] - 1, nc = ncs[seg], sgf = sgfs[seg];
+            named_bar_sync(2 + seg, MV_CONSUMER_WARPS * 32 + 32);  // every consumer warp stored its share of this tile
+            if (p.trace && lane == 0) p.trace[g * 8 + 5] = globaltimer_ns();
+            unsigned int old = 0;
+            if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.ws_cnt + tq) : "memory");
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (p.trace && lane == 0) p.trace[g * 8 + 6] = globaltimer_ns();
+            if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
+            // last arriver: sum the partials in CTA order (deterministic), 4 contributors' loads in flight at a time
+            for (int v = 0; v < MB; v++) {
+                const int idx = (v * 32 + lane) * 4;
+                float4 sum = __ldcg(reinterpret_cast<const float4*>(p.ws_part + ((size_t)gf * 2 + sgf) * (TILE_ROWS * MB) + idx));
+                for (int g0 = (int)gf + 1; g0 <= (int)gl; g0 += 4) {
+                    float4 t4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (g0 + u <= (int)gl) t4[u] = __ldcg(reinterpret_cast<const float4*>(p.ws_part + ((size_t)(g0 + u) * 2) * (TILE_ROWS * MB) + idx));
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (g0 + u <= (int)gl) { sum.x += t4[u].x; sum.y += t4[u].y; sum.z += t4[u].z; sum.w += t4[u].w; }
+                }
+                const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int rr = (idx + e) / MB, m = (idx + e) % MB;
+                    const int64_t n = tq * TILE_ROWS + rr;
+                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, sv[e] + (p.bias ? p.bias[n] : 0.0f));
+                }
+            }
+            if (lane == 0) p.ws_cnt[tq] = 0u;
+            if (p.trace && lane == 0) p.trace[g * 8 + 7] = globaltimer_ns();
         }
         return;
     }
 
     // ===================== consumers =====================
+    pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
     const int g4 = lane >> 3, i = lane & 7;
     const FmtMeta meta{p.gpc};
-    float acc[4][MB];
+    float acc[MV_STEPS][MB];
 #pragma unroll
-    for (int s4 = 0; s4 < 4; s4++)
+    for (int s4 = 0; s4 < MV_STEPS; s4++)
 #pragma unroll
         for (int m = 0; m < MB; m++) acc[s4][m] = 0.0f;
 
-    int64_t it = 0;
-    for (int64_t c = c0; c < c1; c++, it++) {
-        const int s = (int)(it % nst);
-        const uint32_t round = (uint32_t)(it / nst);
-        mbar_wait(&full[s], round & 1u);
+    // segment walk: 0 = head (partial, slot 0), 1 = tail (partial, slot 1), 2 = full tiles
+    int seg = sp.nH > 0 ? 0 : (sp.nT > 0 ? 1 : 2);
+    int seg_left = seg == 0 ? sp.nH : (seg == 1 ? sp.nT : KC);  // chunks until the next flush
+    int t = seg == 0 ? sp.tH : (seg == 1 ? sp.tT : sp.tF);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_chunks; j++) {
+        mbar_wait(&full[s], ph);
+        if (p.trace && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
         const uint8_t* wc = stages + (size_t)s * p.stage_bytes;
         const uint8_t* xr = wc + p.chunk_bytes;
 
@@ -111,9 +237,10 @@ __global__ void __launch_bounds__(MV_THREADS, (MB <= 2 ? 2 : 1)) matvec_kernel(c
             bsA[m] = (int)(int16_t)(bs & 0xFFFFu);
             bsB[m] = (int)(int16_t)(bs >> 16);
         }
+        if (!(p.debug_flags & 1))
 #pragma unroll
-        for (int s4 = 0; s4 < 4; s4++) {
-            const int r = 16 * warp + 4 * s4 + g4;
+        for (int s4 = 0; s4 < MV_STEPS; s4++) {
+            const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
             Unit u;
             F::template load_unit<true>(wc, r, i, u, meta);
 #pragma unroll
@@ -125,84 +252,68 @@ __global__ void __launch_bounds__(MV_THREADS, (MB <= 2 ? 2 : 1)) matvec_kernel(c
                 sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
                 sA -= u.off[0] * bsA[m];
                 sB -= u.off[1] * bsB[m];
-                float t = (u.a[0] * dx[m]) * (float)sA + (u.a[1] * dx[m]) * (float)sB;
-                if (F::HAS_MIN) t -= (u.b[0] * dx[m]) * (float)bsA[m] + (u.b[1] * dx[m]) * (float)bsB[m];
-                acc[s4][m] += t;
+                float tt = (u.a[0] * dx[m]) * (float)sA + (u.a[1] * dx[m]) * (float)sB;
+                if (F::HAS_MIN) tt -= (u.b[0] * dx[m]) * (float)bsA[m] + (u.b[1] * dx[m]) * (float)bsB[m];
+                acc[s4][m] += tt;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == nst) { s = 0; ph ^= 1u; }
 
-        // ---- tile boundary: flush ----
-        const bool tile_end = ((c + 1) % p.KC == 0) || (c + 1 == c1);
-        if (tile_end) {
-            const int64_t t = c / p.KC;
+        if (--seg_left > 0) continue;
+
+        // ---- segment / tile boundary: reduce the 8 lanes of each row and flush ----
 #pragma unroll
-            for (int s4 = 0; s4 < 4; s4++)
+        for (int s4 = 0; s4 < MV_STEPS; s4++)
 #pragma unroll
-                for (int m = 0; m < MB; m++) {
-                    float v = acc[s4][m];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    acc[s4][m] = v;
-                }
-            const bool full_tile = (c0 <= t * p.KC) && ((t + 1) * p.KC <= c1);
-            if (full_tile) {
-                if (i == 0) {
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) {
-                        const int64_t n = t * TILE_ROWS + 16 * warp + 4 * s4 + g4;
-                        if (n < p.N) {
-                            const float bv = p.bias ? p.bias[n] : 0.0f;
-#pragma unroll
-                            for (int m = 0; m < MB; m++)
-                                if (m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, acc[s4][m] + bv);
-                        }
-                    }
-                }
-            } else {
-                const int slot = (t == c0 / p.KC) ? 0 : 1;
-                float* part = p.ws_part + ((size_t)g * 2 + slot) * (TILE_ROWS * MB);
-                if (i == 0) {
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) {
-                        const int rr = 16 * warp + 4 * s4 + g4;
-#pragma unroll
-                        for (int m = 0; m < MB; m++) part[rr * MB + m] = acc[s4][m];
-                    }
-                    __threadfence();
-                }
-                named_bar_sync(1, MV_CONSUMER_WARPS * 32);
-                const int64_t gf = sk_owner(t * p.KC, p.C, G), gl = sk_owner((t + 1) * p.KC - 1, p.C, G);
-                if (tid == 0) {
-                    __threadfence();
-                    unsigned int old = atomicAdd(&p.ws_cnt[t], 1u);
-                    *sflag = (old == (unsigned int)(gl - gf)) ? 1 : 0;
-                }
-                named_bar_sync(1, MV_CONSUMER_WARPS * 32);
-                if (*sflag) {
-                    __threadfence();
-                    for (int idx = tid; idx < TILE_ROWS * MB; idx += MV_CONSUMER_WARPS * 32) {
-                        float sum = 0.0f;
-                        for (int64_t gg = gf; gg <= gl; gg++) {
-                            const int sl = (sk_begin(gg, p.C, G) / p.KC == t) ? 0 : 1;
-                            sum += __ldcg(p.ws_part + ((size_t)gg * 2 + sl) * (TILE_ROWS * MB) + idx);
-                        }
-                        const int rr = idx / MB, m = idx % MB;
-                        const int64_t n = t * TILE_ROWS + rr;
-                        if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, sum + (p.bias ? p.bias[n] : 0.0f));
-                    }
-                    if (tid == 0) p.ws_cnt[t] = 0u;
-                }
-                named_bar_sync(1, MV_CONSUMER_WARPS * 32);
+            for (int m = 0; m < MB; m++) {
+                float v = acc[s4][m];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                acc[s4][m] = v;
             }
+        if (seg == 2) {
+            if (i == 0) {
 #pragma unroll
-            for (int s4 = 0; s4 < 4; s4++)
+                for (int s4 = 0; s4 < MV_STEPS; s4++) {
+                    const int64_t n = (int64_t)t * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
+                    if (n < p.N) {
+                        const float bv = p.bias ? p.bias[n] : 0.0f;
 #pragma unroll
-                for (int m = 0; m < MB; m++) acc[s4][m] = 0.0f;
+                        for (int m = 0; m < MB; m++)
+                            if (m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, acc[s4][m] + bv);
+                    }
+                }
+            }
+        } else {
+            // partial tile: publish my share, then (warp 0) announce the arrival with a release atomic
+            float* part = p.ws_part + ((size_t)g * 2 + seg) * (TILE_ROWS * MB);
+            if (i == 0) {
+#pragma unroll
+                for (int s4 = 0; s4 < MV_STEPS; s4++) {
+                    const int rr = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
+#pragma unroll
+                    for (int m = 0; m < MB; m++) part[rr * MB + m] = acc[s4][m];
+                }
+                __threadfence_block();
+            }
+            __syncwarp();
+            asm volatile("bar.arrive %0, %1;" ::"r"(2 + seg), "r"(MV_CONSUMER_WARPS * 32 + 32) : "memory");
         }
+#pragma unroll
+        for (int s4 = 0; s4 < MV_STEPS; s4++)
+#pragma unroll
+            for (int m = 0; m < MB; m++) acc[s4][m] = 0.0f;
+
+        // ---- next segment / tile ----
+        if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; }
+        else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; }
+        else { seg_left = KC; t++; }
+
     }
+    if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -218,7 +329,18 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    matvec_kernel<F, MB><<<grid, MV_THREADS, smem, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(MV_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap with the predecessor's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB>, p);
+    if (le != cudaSuccess) return le;
     count_launch();
     return cudaGetLastError();
 }
@@ -233,18 +355,23 @@ static cudaError_t launch_f(const MatvecParams& p, int mb, int grid, int smem, c
     }
 }
 
+static long long* g_trace = nullptr;
+static int g_trace_launch = 0;
+void set_matvec_trace(long long* p) { g_trace = p; g_trace_launch = 0; }
+
 cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan) {
     if (M < 1 || M > 4) return cudaErrorInvalidValue;
     int mb = M == 1 ? 1 : (M == 2 ? 2 : 4);
     int stage = w->chunk_bytes + (int)M * ACT_REC_BYTES;
     stage = (stage + 127) & ~127;
-    int budget = 108 * 1024 - MV_HDR_BYTES;
+    int budget = 110 * 1024 - MV_HDR_BYTES;  // half an SM: the next kernel's CTA co-resides and prefetches (PDL)
     int nst = budget / stage;
     if (nst > MV_MAX_STAGES) nst = MV_MAX_STAGES;
+    if (const char* e = getenv("B200Q_MV_STAGES")) { int v = atoi(e); if (v >= 2 && v < nst) nst = v; }
     if (nst < 2) return cudaErrorInvalidValue;
     int64_t C = w->T * w->KC;
-    int ctas_per_sm = (mb <= 2) ? 2 : 1;
-    int64_t G = (int64_t)w->num_sms * ctas_per_sm;
+    int64_t G = (int64_t)w->num_sms;
+    if (const char* e = getenv("B200Q_MV_GRID")) { int v = atoi(e); if (v >= 1) G = v; }
     if (G > C) G = C;
     plan->grid = (int)G;
     plan->nstages = nst;
@@ -257,7 +384,7 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan) {
 size_t matvec_ws_bytes(const b200q_weight* w, int64_t M) {
     // counters (one per row tile, padded) + 2 partial slots per potential CTA
     size_t cnt = ((size_t)w->T * 4 + 255) & ~(size_t)255;
-    size_t part = (size_t)w->num_sms * 2 * 2 * TILE_ROWS * 4 * sizeof(float);
+    size_t part = (size_t)w->num_sms * 2 * TILE_ROWS * 4 * sizeof(float);
     (void)M;
     return cnt + part;
 }
@@ -284,6 +411,16 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.nstages = plan.nstages;
     p.chunk_bytes = w->chunk_bytes;
     p.stage_bytes = plan.stage_bytes;
+    p.trace = g_trace ? g_trace + (size_t)(g_trace_launch++) * 148 * 8 : nullptr;
+    p.debug_flags = 0;
+    {
+        // L2 prefetch budget: at most ~64 MB per launch so a huge weight (lm_head) cannot thrash the 126 MB L2
+        int64_t per_cta = (64ll << 20) / ((int64_t)plan.grid * p.chunk_bytes);
+        p.l2_prefetch_chunks = 0;  // measured: prefetching into L2 from here delays the x copy and slows the predecessor (r1 notes)
+        (void)per_cta;
+        if (const char* e = getenv("B200Q_MV_L2PF")) p.l2_prefetch_chunks = atoi(e);
+    }
+    if (const char* e = getenv("B200Q_MV_DEBUG")) p.debug_flags = atoi(e);
     switch (w->family) {
         case B200Q_FAM_Q4_K: return launch_f<FmtQ4K>(p, plan.mb, plan.grid, plan.smem_bytes, st);
         case B200Q_FAM_Q6_K: return launch_f<FmtQ6K>(p, plan.mb, plan.grid, plan.smem_bytes, st);

@@ -114,3 +114,51 @@ def test_stream_k_partition_formulae():
         for g in range(G):
             for c in {begins[g], begins[g + 1] - 1}:
                 assert _sk_owner(c, C_, G) == g
+
+
+def _sk_plan(c0, c1, KC):
+    """python mirror of matvec.cu sk_plan()"""
+    t0, t1 = c0 // KC, (c1 - 1) // KC
+    kc0 = c0 - t0 * KC
+    if kc0 != 0 or c1 < (t0 + 1) * KC:
+        head_end = min((t0 + 1) * KC, c1)
+    else:
+        head_end = c0
+    nH = head_end - c0
+    tail_begin = c1
+    if c1 > head_end and c1 != (t1 + 1) * KC:
+        tail_begin = max(t1 * KC, head_end)
+    nT = c1 - tail_begin
+    nF = tail_begin - head_end
+    return dict(nH=nH, nT=nT, nF=nF, kcH=kc0, tH=t0, tT=t1, tF=head_end // KC, head_end=head_end, tail_begin=tail_begin)
+
+
+def test_stream_k_segment_plan():
+    """head / tail / full segmentation: covers the range once, full segment is whole tiles, and the slot a
+    contributor writes (head=0, tail=1) is the slot the reducer reads (first contributor: 0 iff it starts on
+    the tile boundary, every later contributor: 0)."""
+    rng = np.random.default_rng(1)
+    cases = [(16, 112, 148), (16, 32, 148), (16, 224, 148), (56, 32, 148), (1, 100, 148), (112, 1, 148), (8, 4, 148), (3, 7, 5)]
+    cases += [(int(k), int(t), int(g)) for k, t, g in zip(rng.integers(1, 120, 30), rng.integers(1, 300, 30), rng.integers(1, 300, 30))]
+    for KC, T, G in cases:
+        C_ = KC * T
+        G = min(G, C_)
+        contrib = {}
+        for g in range(G):
+            c0, c1 = _sk_begin(g, C_, G), _sk_begin(g + 1, C_, G)
+            sp = _sk_plan(c0, c1, KC)
+            assert sp["nH"] >= 0 and sp["nT"] >= 0 and sp["nF"] >= 0
+            assert sp["nH"] + sp["nT"] + sp["nF"] == c1 - c0
+            assert sp["nF"] % KC == 0 and (sp["nF"] == 0 or sp["head_end"] % KC == 0)
+            if sp["nH"]:
+                assert sp["nH"] < KC and (c0 + sp["nH"] - 1) // KC == sp["tH"]
+                contrib.setdefault(sp["tH"], []).append((g, 0))
+            if sp["nT"]:
+                assert sp["nT"] < KC and sp["tail_begin"] % KC == 0 and sp["tail_begin"] // KC == sp["tT"]
+                contrib.setdefault(sp["tT"], []).append((g, 1))
+        for t, lst in contrib.items():
+            gf, gl = _sk_owner(t * KC, C_, G), _sk_owner((t + 1) * KC - 1, C_, G)
+            assert [g for g, _ in lst] == list(range(gf, gl + 1)), (KC, T, G, t, lst)
+            slot_gf = 0 if _sk_begin(gf, C_, G) == t * KC else 1
+            assert lst[0][1] == slot_gf and all(sl == 0 for _, sl in lst[1:])
+            assert len(lst) >= 2  # a tile with a single contributor is never "partial"
