@@ -68,6 +68,23 @@ __device__ __forceinline__ long long globaltimer_ns() {
     return t;
 }
 
+// Deterministic expf: only IEEE add/mul/fma in a fixed order, mirrored line by line by oracle/quant_oracle.c
+// orc_det_expf, so activations downstream of softmax / SiLU are bit-reproducible against the CPU oracle.
+__device__ __forceinline__ float det_expf(float x) {
+    x = fminf(fmaxf(x, -87.0f), 88.0f);
+    const float n = rintf(__fmul_rn(x, 1.44269504f));
+    float r = fmaf(n, -0.693145752f, x);
+    r = fmaf(n, -1.42860677e-6f, r);
+    float p = 1.0f / 720.0f;
+    p = fmaf(p, r, 1.0f / 120.0f);
+    p = fmaf(p, r, 1.0f / 24.0f);
+    p = fmaf(p, r, 1.0f / 6.0f);
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    return __fmul_rn(p, __int_as_float(((int)n + 127) << 23));
+}
+
 // ---- programmatic dependent launch ----
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

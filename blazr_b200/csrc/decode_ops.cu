@@ -1,0 +1,304 @@
+// decode_ops.cu -- the small operators that sit between the quantized matvecs of one decode step
+// (norm -> activation-quant, RoPE + KV append + decode attention, SwiGLU,
+// residual, lm_head argmax).  They are NOT the graded hot path; they exist so that a whole decode step can
+// be captured in one CUDA graph and timed as tokens/s, and each one emits the int8 activation records the
+// next matvec consumes (so no separate quantise pass runs).  Every kernel is PDL-aware: it lets its
+// dependents launch immediately (the following matvec prefetches weights meanwhile) and waits for its own
+// producers before touching global memory.
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200q {
+
+// ---- shared: quantise 256 values held one per thread (thread t <-> k = kc*256 + t) into a record ----
+__device__ __forceinline__ void quant_store_record(float v, uint8_t* rec, int t) {
+    const int wid = t >> 5, lane = t & 31;
+    float amax = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float d = __fdiv_rn(amax, 127.0f);
+    const int q = (amax == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v, d));
+    int s = q;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int s_hi = __shfl_sync(0xffffffffu, s, 16);
+    rec[t] = (uint8_t)(int8_t)q;
+    if (lane == 0) {
+        reinterpret_cast<float*>(rec + 256)[wid] = d;
+        reinterpret_cast<uint32_t*>(rec + 288)[wid] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
+    }
+}
+
+template <typename... Args>
+static cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    count_launch();
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// h (+= delta) ; xq = quant(rmsnorm(h) * w)          one CTA of 256 threads per token row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(float* __restrict__ h, const float* __restrict__ delta, const float* __restrict__ w,
+                                                                 float eps, int H, int M, uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int m = blockIdx.x, t = threadIdx.x;
+    float* hr = h + (size_t)m * H;
+    __shared__ double red[8];
+    double ss = 0.0;  // f64: exact squares, order-independent sum -> bit-reproducible against the oracle
+    for (int k = t; k < H; k += 256) {
+        float v = hr[k];
+        if (delta) { v = __fadd_rn(v, delta[(size_t)m * H + k]); hr[k] = v; }
+        ss = fma((double)v, (double)v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((t & 31) == 0) red[t >> 5] = ss;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)H), eps)));
+    const int KCn = H / CHUNK_K;
+    for (int kc = 0; kc < KCn; kc++) {
+        const int k = kc * CHUNK_K + t;
+        const float v = __fmul_rn(__fmul_rn(hr[k], inv), w[k]);
+        if (xnorm) xnorm[(size_t)m * H + k] = v;
+        quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// act = silu(gate) * up ; xq = quant(act)       gate_up: [M, 2*F] (gate first), F % 256 == 0
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restrict__ gu, int F, int M, uint8_t* __restrict__ xq) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
+    const int k = kc * CHUNK_K + t;
+    const float g = gu[(size_t)m * 2 * F + k], u = gu[(size_t)m * 2 * F + F + k];
+    const float v = __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, det_expf(-g))), u);
+    quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (adjacent pairs, cos/sin from a host-built table) + KV append + single-query attention + output quant.
+// Two passes with f64 reductions and the deterministic exp, so the result is bit-reproducible against the
+// oracle:  s_j = f32(sum_e q_e k_je) * scale;  p_j = det_exp(s_j - max);  o_e = f32(sum_j p_j v_je) / f32(sum_j p_j).
+// qkv: [M, (nh + 2 nkv) * hd] f32; cache_k/v: [M seqs][max_ctx][nkv][hd] f32; pos[m] = position of the new
+// token; rope: [max_ctx][hd/2][2] (cos, sin).  One CTA of 128 threads per (head, m); dynamic smem = max_ctx f32.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos, float* __restrict__ cache_k,
+                                                           float* __restrict__ cache_v, const float* __restrict__ rope, int nh, int nkv,
+                                                           int max_ctx, int M, uint8_t* __restrict__ xq, float* __restrict__ attn_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float s_sc[];  // scores, then probabilities, for positions 0..p
+    constexpr int EPL = HD / 32;
+    const int head = blockIdx.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int kvh = head / (nh / nkv);
+    const int p = pos[m];
+    const int row = (nh + 2 * nkv) * HD;
+    const float* qsrc = qkv + (size_t)m * row + (size_t)head * HD;
+    const float* ksrc = qkv + (size_t)m * row + (size_t)(nh + kvh) * HD;
+    const float* vsrc = qkv + (size_t)m * row + (size_t)(nh + nkv + kvh) * HD;
+    float* ck = cache_k + ((size_t)m * max_ctx) * nkv * HD + (size_t)kvh * HD;
+    float* cv = cache_v + ((size_t)m * max_ctx) * nkv * HD + (size_t)kvh * HD;
+    const size_t pstride = (size_t)nkv * HD;
+    const float* rt = rope + (size_t)p * HD;  // [hd/2][2]
+
+    __shared__ float sq[HD], sk[HD], sv[HD];
+    __shared__ float s_redf[4];
+    __shared__ double s_redd[4];
+    if (t < HD / 2) {
+        const float c = rt[2 * t], sn = rt[2 * t + 1];
+        const float q0 = qsrc[2 * t], q1 = qsrc[2 * t + 1];
+        sq[2 * t] = __fsub_rn(__fmul_rn(q0, c), __fmul_rn(q1, sn));
+        sq[2 * t + 1] = __fadd_rn(__fmul_rn(q0, sn), __fmul_rn(q1, c));
+        const float k0 = ksrc[2 * t], k1 = ksrc[2 * t + 1];
+        const float r0 = __fsub_rn(__fmul_rn(k0, c), __fmul_rn(k1, sn)), r1 = __fadd_rn(__fmul_rn(k0, sn), __fmul_rn(k1, c));
+        sk[2 * t] = r0; sk[2 * t + 1] = r1;
+        sv[2 * t] = vsrc[2 * t]; sv[2 * t + 1] = vsrc[2 * t + 1];
+        if (head % (nh / nkv) == 0) {  // one head of each kv group appends the new k, v
+            ck[(size_t)p * pstride + 2 * t] = r0; ck[(size_t)p * pstride + 2 * t + 1] = r1;
+            cv[(size_t)p * pstride + 2 * t] = vsrc[2 * t]; cv[(size_t)p * pstride + 2 * t + 1] = vsrc[2 * t + 1];
+        }
+    }
+    __syncthreads();
+    // ---- pass 1: scores ----
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
+    float lmax = -INFINITY;
+    for (int j = warp; j <= p; j += 4) {
+        double d = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+            const int idx = lane * EPL + e;
+            const float kk = (j < p) ? ck[(size_t)j * pstride + idx] : sk[idx];  // the new key comes from smem: no wait on the appending CTA
+            d = fma((double)sq[idx], (double)kk, d);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        const float sc = __fmul_rn((float)d, scale);
+        if (lane == 0) s_sc[j] = sc;
+        lmax = fmaxf(lmax, sc);
+    }
+    if (lane == 0) s_redf[warp] = lmax;
+    __syncthreads();
+    const float gmax = fmaxf(fmaxf(s_redf[0], s_redf[1]), fmaxf(s_redf[2], s_redf[3]));
+    double lsum = 0.0;
+    for (int j = t; j <= p; j += 128) {
+        const float pj = det_expf(__fsub_rn(s_sc[j], gmax));
+        s_sc[j] = pj;
+        lsum += (double)pj;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if (lane == 0) s_redd[warp] = lsum;
+    __syncthreads();
+    const float den = (float)(s_redd[0] + s_redd[1] + s_redd[2] + s_redd[3]);
+    // ---- pass 2: thread t owns output element t ----
+    float outv = 0.0f;
+    if (t < HD) {
+        double o = 0.0;
+        for (int j = 0; j < p; j++) o = fma((double)s_sc[j], (double)cv[(size_t)j * pstride + t], o);
+        o = fma((double)s_sc[p], (double)sv[t], o);
+        outv = __fdiv_rn((float)o, den);
+        if (attn_out) attn_out[(size_t)m * nh * HD + (size_t)head * HD + t] = outv;
+        // quantise this head's HD outputs into the o_proj activation records (32-blocks never straddle heads)
+        const int kglob = head * HD + t;
+        const int kc = kglob / CHUNK_K, tin = kglob % CHUNK_K;
+        uint8_t* rec = xq + ((size_t)kc * M + m) * ACT_REC_BYTES;
+        float amax = fabsf(outv);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        const float d = __fdiv_rn(amax, 127.0f);
+        const int q = (amax == 0.0f) ? 0 : (int)roundf(__fdiv_rn(outv, d));
+        int s = q;
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const int s_hi = __shfl_sync(0xffffffffu, s, 16);
+        rec[tin] = (uint8_t)(int8_t)q;
+        if (lane == 0) {
+            reinterpret_cast<float*>(rec + 256)[tin >> 5] = d;
+            reinterpret_cast<uint32_t*>(rec + 288)[tin >> 5] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy sampling: argmax over the vocabulary, lowest index wins ties.  One CTA of 1024 threads per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int64_t* __restrict__ out, int* __restrict__ pos_inc) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int m = blockIdx.x, t = threadIdx.x;
+    const float* row = logits + (size_t)m * V;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = t; i < V; i += 1024) {
+        const float v = row[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    __shared__ float sv[32];
+    __shared__ int si[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((t & 31) == 0) { sv[t >> 5] = best; si[t >> 5] = bi; }
+    __syncthreads();
+    if (t < 32) {
+        best = sv[t]; bi = si[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (t == 0) {
+            out[m] = bi;
+            if (pos_inc) pos_inc[m] += 1;  // advance the sequence position for the next graph replay
+        }
+    }
+}
+
+// embedding gather: h[m, :] = table[ids[m], :] (f16 table -> f32)
+__global__ void embed_kernel(const __half* __restrict__ table, const int64_t* __restrict__ ids, int H, float* __restrict__ h) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int m = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < H) h[(size_t)m * H + k] = __half2float(table[(size_t)ids[m] * H + k]);
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+int32_t b200q_add_rmsnorm_quant(float* h, const float* delta, const float* w, float eps, int64_t H, int64_t M, void* xq, float* xnorm, void* stream) {
+    if (!h || !w || !xq || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)M), dim3(256), 0, (cudaStream_t)stream, h, delta, w, eps, (int)H, (int)M,
+                               (uint8_t*)xq, xnorm);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream) {
+    if (!gate_up || !xq || F <= 0 || F % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)(F / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
+                               (int)M, (uint8_t*)xq);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table, int32_t n_heads,
+                          int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq, float* attn_out, void* stream) {
+    if (!qkv || !pos || !cache_k || !cache_v || !rope_table || !xq || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || M <= 0 || max_ctx <= 0)
+        return B200Q_ERR_INVALID_ARG;
+    if (((int64_t)n_heads * head_dim) % CHUNK_K) return B200Q_ERR_INVALID_ARG;
+    if ((size_t)max_ctx * 4 > 160 * 1024) return B200Q_ERR_UNSUPPORTED;
+    cudaError_t e;
+    dim3 grid((unsigned)n_heads, (unsigned)M);
+    size_t smem = (size_t)max_ctx * sizeof(float);
+    if (head_dim == 128) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = launch_pdl(attn_decode_kernel<128>, grid, dim3(128), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
+                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out);
+    } else if (head_dim == 64) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = launch_pdl(attn_decode_kernel<64>, grid, dim3(128), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
+                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out);
+    } else {
+        return B200Q_ERR_UNSUPPORTED;
+    }
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+int32_t b200q_argmax(const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream) {
+    if (!logits || !out_ids || V <= 0 || M <= 0) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(argmax_kernel, dim3((unsigned)M), dim3(1024), 0, (cudaStream_t)stream, logits, (int)V, out_ids, (int*)pos_inc);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+int32_t b200q_embed(const void* table_f16, const int64_t* ids, int64_t H, int64_t M, float* h, void* stream) {
+    if (!table_f16 || !ids || !h || H <= 0 || M <= 0) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(embed_kernel, dim3((unsigned)((H + 255) / 256), (unsigned)M), dim3(256), 0, (cudaStream_t)stream,
+                               (const __half*)table_f16, ids, (int)H, h);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -31,7 +31,7 @@ struct MatvecParams {
     const uint8_t* xq;
     void* y;
     const float* bias;
-    float* ws_part;
+    double* ws_part;
     unsigned int* ws_cnt;
     int64_t N;
     int M, y_dtype;
@@ -176,24 +176,24 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
             if (p.trace && lane == 0) p.trace[g * 8 + 6] = globaltimer_ns();
             if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
             // last arriver: sum the partials in CTA order (deterministic), 4 contributors' loads in flight at a time
-            for (int v = 0; v < MB; v++) {
-                const int idx = (v * 32 + lane) * 4;
-                float4 sum = __ldcg(reinterpret_cast<const float4*>(p.ws_part + ((size_t)gf * 2 + sgf) * (TILE_ROWS * MB) + idx));
-                for (int g0 = (int)gf + 1; g0 <= (int)gl; g0 += 4) {
-                    float4 t4[4];
+            for (int v = 0; v < 2 * MB; v++) {
+                const int idx = (v * 32 + lane) * 2;  // 128*MB doubles per partial, 2 per lane per pass
+                double2 sum = __ldcg(reinterpret_cast<const double2*>(p.ws_part + ((size_t)gf * 2 + sgf) * (TILE_ROWS * MB) + idx));
+                for (int g0 = gf + 1; g0 <= gl; g0 += 4) {
+                    double2 t4[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++)
-                        if (g0 + u <= (int)gl) t4[u] = __ldcg(reinterpret_cast<const float4*>(p.ws_part + ((size_t)(g0 + u) * 2) * (TILE_ROWS * MB) + idx));
+                        if (g0 + u <= gl) t4[u] = __ldcg(reinterpret_cast<const double2*>(p.ws_part + ((size_t)(g0 + u) * 2) * (TILE_ROWS * MB) + idx));
 #pragma unroll
                     for (int u = 0; u < 4; u++)
-                        if (g0 + u <= (int)gl) { sum.x += t4[u].x; sum.y += t4[u].y; sum.z += t4[u].z; sum.w += t4[u].w; }
+                        if (g0 + u <= gl) { sum.x += t4[u].x; sum.y += t4[u].y; }
                 }
-                const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+                const double sv[2] = {sum.x, sum.y};
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
+                for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
                     const int64_t n = tq * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, sv[e] + (p.bias ? p.bias[n] : 0.0f));
+                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, (float)(sv[e] + (p.bias ? (double)p.bias[n] : 0.0)));
                 }
             }
             if (lane == 0) p.ws_cnt[tq] = 0u;
@@ -206,11 +206,14 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
     pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
     const int g4 = lane >> 3, i = lane & 7;
     const FmtMeta meta{p.gpc};
-    float acc[MV_STEPS][MB];
+    // f64 accumulators: every term is an exact product of an f32 scale and an integer partial, so the sum is
+    // independent of the summation order up to 1e-16 -> the result is bit-reproducible against the oracle for any
+    // grid size / stream-K split (oracle orc_matmul_q8).
+    double acc[MV_STEPS][MB];
 #pragma unroll
     for (int s4 = 0; s4 < MV_STEPS; s4++)
 #pragma unroll
-        for (int m = 0; m < MB; m++) acc[s4][m] = 0.0f;
+        for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
 
     // segment walk: 0 = head (partial, slot 0), 1 = tail (partial, slot 1), 2 = full tiles
     int seg = sp.nH > 0 ? 0 : (sp.nT > 0 ? 1 : 2);
@@ -252,9 +255,17 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
                 sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
                 sA -= u.off[0] * bsA[m];
                 sB -= u.off[1] * bsB[m];
-                float tt = (u.a[0] * dx[m]) * (float)sA + (u.a[1] * dx[m]) * (float)sB;
-                if (F::HAS_MIN) tt -= (u.b[0] * dx[m]) * (float)bsA[m] + (u.b[1] * dx[m]) * (float)bsB[m];
-                acc[s4][m] += tt;
+                double a_ = acc[s4][m];
+                if (F::SUB == 32) {  // one scale per 32 weights
+                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), (double)(sA + sB), a_);
+                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), (double)(bsA[m] + bsB[m]), a_);
+                } else {             // two 16-wide sub-blocks with their own scales
+                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), (double)sA, a_);
+                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), (double)bsA[m], a_);
+                    a_ = fma((double)__fmul_rn(u.a[1], dx[m]), (double)sB, a_);
+                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[1], dx[m]), (double)bsB[m], a_);
+                }
+                acc[s4][m] = a_;
             }
         }
         __syncwarp();
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
         for (int s4 = 0; s4 < MV_STEPS; s4++)
 #pragma unroll
             for (int m = 0; m < MB; m++) {
-                float v = acc[s4][m];
+                double v = acc[s4][m];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -280,16 +291,16 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
                     const int64_t n = (int64_t)t * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
                     if (n < p.N) {
-                        const float bv = p.bias ? p.bias[n] : 0.0f;
+                        const double bv = p.bias ? (double)p.bias[n] : 0.0;
 #pragma unroll
                         for (int m = 0; m < MB; m++)
-                            if (m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, acc[s4][m] + bv);
+                            if (m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, (float)(acc[s4][m] + bv));
                     }
                 }
             }
         } else {
             // partial tile: publish my share, then (warp 0) announce the arrival with a release atomic
-            float* part = p.ws_part + ((size_t)g * 2 + seg) * (TILE_ROWS * MB);
+            double* part = p.ws_part + ((size_t)g * 2 + seg) * (TILE_ROWS * MB);
             if (i == 0) {
 #pragma unroll
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++)
 #pragma unroll
-            for (int m = 0; m < MB; m++) acc[s4][m] = 0.0f;
+            for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
 
         // ---- next segment / tile ----
         if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; }
@@ -384,7 +395,7 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan) {
 size_t matvec_ws_bytes(const b200q_weight* w, int64_t M) {
     // counters (one per row tile, padded) + 2 partial slots per potential CTA
     size_t cnt = ((size_t)w->T * 4 + 255) & ~(size_t)255;
-    size_t part = (size_t)w->num_sms * 2 * TILE_ROWS * 4 * sizeof(float);
+    size_t part = (size_t)w->num_sms * 2 * TILE_ROWS * 4 * sizeof(double);
     (void)M;
     return cnt + part;
 }
@@ -400,7 +411,7 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.bias = w->bias;
     size_t cnt = ((size_t)w->T * 4 + 255) & ~(size_t)255;
     p.ws_cnt = reinterpret_cast<unsigned int*>(ws);
-    p.ws_part = reinterpret_cast<float*>(ws + cnt);
+    p.ws_part = reinterpret_cast<double*>(ws + cnt);
     p.N = w->N;
     p.M = (int)M;
     p.y_dtype = y_dtype;

@@ -1,0 +1,379 @@
+"""Random-init Llama-family decode harness: drives the quantized matvec kernels through one whole decode
+step (the caller pattern of reference src/engine/executor_generate.rs:362-405 and the captured step of
+src/engine/cuda_graphs.rs:101-189), so kernel GB/s turns into tokens/s.
+
+Per layer (batch-1..4 decode, everything enqueued on one stream, PDL-chained, graph-capturable):
+    add+rmsnorm+quant -> [q|k|v] matvec(s) -> RoPE+KV-append+attention+quant -> o matvec
+    add+rmsnorm+quant -> [gate|up] matvec(s) -> SwiGLU+quant -> down matvec
+then add+rmsnorm+quant -> lm_head matvec -> argmax (greedy, the configs' sampling mode).
+
+Projections of equal format are fused at upload (q,k,v / gate,up share one weight handle, i.e. one launch);
+the GGUF "Q4_K_M" mix keeps attn_v / ffn_down of the "more bits" layers in Q6_K.
+Tensor parallel (reference src/engine/tensor_parallel.rs, Megatron split): column-split q/k/v/gate/up by
+heads / rows, row-split o/down along K at block granularity, all-reduce after o and down, vocab-split
+lm_head + all-gather.
+
+PyTorch is plumbing only (buffers, streams, NCCL); all math runs in libb200q kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops, synth
+
+
+@dataclass
+class ModelConfig:
+    name: str
+    hidden: int
+    n_layers: int
+    n_heads: int
+    n_kv_heads: int
+    head_dim: int
+    ffn: int
+    vocab: int
+    rope_theta: float = 10000.0
+    eps: float = 1e-5
+
+
+PRESETS: Dict[str, ModelConfig] = {
+    "llama-3.2-1b": ModelConfig("llama-3.2-1b", 2048, 16, 32, 8, 64, 8192, 128256, 500000.0),
+    "mistral-7b": ModelConfig("mistral-7b", 4096, 32, 32, 8, 128, 14336, 32000, 10000.0),
+    "llama-3-8b": ModelConfig("llama-3-8b", 4096, 32, 32, 8, 128, 14336, 128256, 500000.0),
+    "llama-3-70b": ModelConfig("llama-3-70b", 8192, 80, 64, 8, 128, 28672, 128256, 500000.0),
+    # reduced shapes for tests (same structure, seconds on the CPU oracle)
+    "tiny": ModelConfig("tiny", 512, 2, 8, 2, 64, 1024, 2048, 10000.0),
+    "small-1b": ModelConfig("small-1b", 2048, 4, 32, 8, 64, 8192, 16384, 500000.0),
+}
+
+
+def rope_table(max_ctx: int, head_dim: int, theta: float) -> np.ndarray:
+    """[max_ctx, hd/2, 2] f32 (cos, sin) of pos * theta^(-2i/hd), computed in f64 and rounded once.  The same
+    formula is restated in oracle/model.py; a table (instead of device powf/sincos) keeps RoPE bit-reproducible."""
+    i = np.arange(head_dim // 2, dtype=np.float64)
+    freq = np.power(float(theta), -2.0 * i / head_dim)
+    ang = np.arange(max_ctx, dtype=np.float64)[:, None] * freq[None, :]
+    return np.stack([np.cos(ang), np.sin(ang)], axis=-1).astype(np.float32)
+
+
+def use_more_bits(i: int, n: int) -> bool:
+    """llama.cpp's layer rule for the *_M mixes (public convention)"""
+    return i < n // 8 or i >= 7 * n // 8 or (i - n // 8) % 3 == 2
+
+
+def layer_formats(cfg: ModelConfig, scheme: str, i: int) -> Dict[str, str]:
+    """format of each projection of layer i under a quantisation scheme"""
+    if scheme == "Q4_K_M":
+        hi = "Q6_K" if use_more_bits(i, cfg.n_layers) else "Q4_K"
+        return dict(q="Q4_K", k="Q4_K", v=hi, o="Q4_K", gate="Q4_K", up="Q4_K", down=hi)
+    return {p: scheme for p in ("q", "k", "v", "o", "gate", "up", "down")}
+
+
+def head_format(scheme: str) -> str:
+    return "Q6_K" if scheme == "Q4_K_M" else scheme
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side random weights (numpy; the oracle consumes the very same arrays)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class HostLinear:
+    fmt: str
+    N: int
+    K: int
+    data: object  # ggml: uint8 [N, row_bytes]; AWQ: (qweight, scales, zeros, gs); GPTQ: (qweight, scales, qzeros, g_idx, gs)
+
+
+@dataclass
+class HostModel:
+    cfg: ModelConfig
+    scheme: str
+    embed: np.ndarray                 # f16 [V, H]
+    layers: List[Dict[str, object]] = field(default_factory=list)  # per layer: HostLinear per projection + norms
+    final_norm: Optional[np.ndarray] = None
+    lm_head: Optional[HostLinear] = None
+
+
+def _host_linear(fmt: str, N: int, K: int, seed: int) -> HostLinear:
+    if fmt in synth.GGML:
+        return HostLinear(fmt, N, K, synth.random_ggml(synth.GGML[fmt], N, K, seed=seed))
+    if fmt == "AWQ":
+        return HostLinear(fmt, N, K, synth.random_awq(N, K, 128, seed=seed) + (128,))
+    if fmt == "GPTQ":
+        qw, sc, qz, gi, _ = synth.random_gptq(N, K, 128, seed=seed)
+        return HostLinear(fmt, N, K, (qw, sc, qz, gi, 128))
+    raise ValueError(fmt)
+
+
+def build_host_model(cfg: ModelConfig, scheme: str, seed: int = 0xB200) -> HostModel:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    hm = HostModel(cfg, scheme, embed=rng.standard_normal((cfg.vocab, cfg.hidden)).astype(np.float16))
+    qd, kvd = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+    shapes = dict(q=(qd, cfg.hidden), k=(kvd, cfg.hidden), v=(kvd, cfg.hidden), o=(cfg.hidden, qd), gate=(cfg.ffn, cfg.hidden),
+                  up=(cfg.ffn, cfg.hidden), down=(cfg.hidden, cfg.ffn))
+    for i in range(cfg.n_layers):
+        fm = layer_formats(cfg, scheme, i)
+        lay: Dict[str, object] = {}
+        for j, (p, (N, K)) in enumerate(shapes.items()):
+            lay[p] = _host_linear(fm[p], N, K, seed + 1000 * (i + 1) + j)
+        lay["attn_norm"] = (1.0 + 0.1 * rng.standard_normal(cfg.hidden)).astype(np.float32)
+        lay["mlp_norm"] = (1.0 + 0.1 * rng.standard_normal(cfg.hidden)).astype(np.float32)
+        hm.layers.append(lay)
+    hm.final_norm = (1.0 + 0.1 * rng.standard_normal(cfg.hidden)).astype(np.float32)
+    hm.lm_head = _host_linear(head_format(scheme), cfg.vocab, cfg.hidden, seed + 999)
+    return hm
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side random ggml blocks (bench: 6-39 GB of weights are generated directly in HBM)
+# ------------------------------------------------------------------------------------------------
+def random_ggml_device(fmt: str, N: int, K: int, seed: int, device) -> torch.Tensor:
+    t = synth.GGML[fmt]
+    be, bb = synth.GGML_SIZES[t]
+    nb = N * (K // be)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    blk = torch.randint(0, 256, (nb, bb), dtype=torch.uint8, device=device, generator=g)
+    d_off, m_off, ratio, std1 = synth._FIELDS[t]
+    sigma = 1.0 / (std1 * float(np.sqrt(K)))
+    d = ((torch.rand(nb, device=device, generator=g) + 0.5) * sigma).to(torch.float16)
+    for o in d_off:
+        blk[:, o:o + 2] = d.view(torch.uint8).reshape(nb, 2)
+    if m_off:
+        mm = (d.float() * ratio).to(torch.float16)
+        for o in m_off:
+            blk[:, o:o + 2] = mm.view(torch.uint8).reshape(nb, 2)
+    return blk.reshape(N, K // be * bb)
+
+
+_NAME_ID = dict(q=1, k=2, v=3, o=4, gate=5, up=6, down=7, lm_head=8)
+
+
+@dataclass
+class _Linear:
+    """one launch: a (possibly fused) weight writing into out[:, col0 : col0 + N]"""
+    w: ops.QuantWeight
+    col0: int
+    ws: torch.Tensor
+
+
+class Decoder:
+    """One rank of a (tensor-parallel) decoder.  `host` gives exact weights (tests); otherwise weights are
+    random blocks generated on the device (bench)."""
+
+    def __init__(self, client: ops.B200Client, cfg: ModelConfig, scheme: str, batch: int = 1, max_ctx: int = 512,
+                 host: Optional[HostModel] = None, seed: int = 0xB200, tp_rank: int = 0, tp_world: int = 1, group=None):
+        assert 1 <= batch <= 4, "the dp4a decode path handles M <= 4 (batched decode uses the GEMM path)"
+        self.c, self.cfg, self.scheme, self.M, self.max_ctx = client, cfg, scheme, batch, max_ctx
+        self.rank, self.world, self.group = tp_rank, tp_world, group
+        dev = client.device
+        self.dev = dev
+        H, hd = cfg.hidden, cfg.head_dim
+        assert cfg.n_heads % tp_world == 0 and cfg.n_kv_heads % tp_world == 0, "heads must divide tp (tensor_parallel.rs:90-101)"
+        self.nh, self.nkv = cfg.n_heads // tp_world, cfg.n_kv_heads // tp_world
+        self.qd, self.kvd = self.nh * hd, self.nkv * hd
+        f0, f1 = ops.shard_range(cfg.ffn, tp_rank, tp_world, granule=256)
+        self.ff = f1 - f0
+        v0, v1 = ops.shard_range(cfg.vocab, tp_rank, tp_world, granule=128)
+        self.v0, self.v1 = v0, v1
+        self.weight_bytes = 0
+        self.layers = []
+        M = batch
+        for i in range(cfg.n_layers):
+            fm = layer_formats(cfg, scheme, i)
+            lay = {}
+            # column-parallel q | k | v (rows of this rank's heads), fused where formats agree
+            lay["qkv"] = self._fused(i, [("q", fm["q"], cfg.n_heads * hd, self.rank * self.qd, self.qd),
+                                         ("k", fm["k"], cfg.n_kv_heads * hd, self.rank * self.kvd, self.kvd),
+                                         ("v", fm["v"], cfg.n_kv_heads * hd, self.rank * self.kvd, self.kvd)], H, host)
+            # row-parallel o: K slice = this rank's heads
+            lay["o"] = self._fused(i, [("o", fm["o"], H, 0, H)], cfg.n_heads * hd, host, kslice=(self.rank * self.qd, (self.rank + 1) * self.qd))
+            lay["gu"] = self._fused(i, [("gate", fm["gate"], cfg.ffn, f0, self.ff), ("up", fm["up"], cfg.ffn, f0, self.ff)], H, host)
+            lay["down"] = self._fused(i, [("down", fm["down"], H, 0, H)], cfg.ffn, host, kslice=(f0, f1))
+            an = host.layers[i]["attn_norm"] if host else np.ones(H, np.float32)
+            mn = host.layers[i]["mlp_norm"] if host else np.ones(H, np.float32)
+            lay["attn_norm"] = torch.from_numpy(an).to(dev)
+            lay["mlp_norm"] = torch.from_numpy(mn).to(dev)
+            lay["ck"] = torch.zeros((M, max_ctx, self.nkv, hd), dtype=torch.float32, device=dev)
+            lay["cv"] = torch.zeros((M, max_ctx, self.nkv, hd), dtype=torch.float32, device=dev)
+            self.layers.append(lay)
+        self.final_norm = torch.from_numpy(host.final_norm if host else np.ones(H, np.float32)).to(dev)
+        self.rope = torch.from_numpy(rope_table(max_ctx, hd, cfg.rope_theta)).to(dev)
+        self.head = self._fused(-1, [("lm_head", head_format(scheme), cfg.vocab, v0, v1 - v0)], H, host)
+        if host is not None:
+            self.embed = torch.from_numpy(host.embed).to(dev)
+        else:
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed + 7)
+            self.embed = torch.randn((cfg.vocab, H), device=dev, generator=g).to(torch.float16)
+        # activations / scratch (all addresses stable: the step is graph-capturable)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.h = torch.zeros((M, H), **f32)
+        self.delta = torch.zeros((M, H), **f32)
+        self.qkv = torch.zeros((M, self.qd + 2 * self.kvd), **f32)
+        self.gu = torch.zeros((M, 2 * self.ff), **f32)
+        self.logits_local = torch.zeros((M, v1 - v0), **f32)
+        self.logits = self.logits_local if tp_world == 1 else torch.zeros((tp_world, M, v1 - v0), **f32)
+        self.ids = torch.zeros(M, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(M, dtype=torch.int32, device=dev)
+        act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
+        self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
+        self.first_step = True
+        self.graph = None
+
+    # ---- weights ------------------------------------------------------------------------------------
+    def _fused(self, layer: int, parts, K: int, host: Optional[HostModel], kslice=None) -> List[_Linear]:
+        """parts: (name, fmt, N_full, row0, nrows).  Consecutive parts of equal format share one handle."""
+        out: List[_Linear] = []
+        col = 0
+        groups = []
+        for p in parts:
+            if groups and groups[-1][0][1] == p[1]:
+                groups[-1].append(p)
+            else:
+                groups.append([p])
+        for grp in groups:
+            fmt = grp[0][1]
+            nrows = sum(p[4] for p in grp)
+            w = self._upload(layer, grp, fmt, K, host, kslice)
+            self.weight_bytes += w.canonical_bytes
+            out.append(_Linear(w, col, w.workspace(self.M)))
+            col += nrows
+        return out
+
+    def _upload(self, layer: int, grp, fmt: str, K: int, host: Optional[HostModel], kslice) -> ops.QuantWeight:
+        k0, k1 = kslice if kslice is not None else (0, K)
+        nrows = sum(p[4] for p in grp)
+        if fmt in synth.GGML:
+            t = synth.GGML[fmt]
+            if host is not None:
+                rows = []
+                for (name, _, _, r0, nr) in grp:
+                    hl = host.lm_head if layer < 0 else host.layers[layer][name]
+                    rows.append(hl.data[r0:r0 + nr])
+                blocks = np.ascontiguousarray(np.concatenate(rows, axis=0))
+            else:
+                seed = 0x5EED + 7919 * (layer + 2) + 131 * _NAME_ID[grp[0][0]] + self.rank
+                if kslice is not None:
+                    return self.c.weight_from_ggml(t, random_ggml_device(fmt, nrows, k1 - k0, seed, self.dev), nrows, k1 - k0)
+                blocks = random_ggml_device(fmt, nrows, K, seed, self.dev)
+            return self.c.weight_from_ggml(t, blocks, nrows, K, cols=(k0, k1) if kslice is not None else None)
+        # AWQ / GPTQ (host models only fuse by concatenating along N)
+        if host is None:
+            host_parts = [_host_linear(fmt, p[4], K, 0x5EED + 31 * (layer + 2) + j + 17 * self.rank) for j, p in enumerate(grp)]
+            sl = [(hp, 0, hp.N) for hp in host_parts]
+        else:
+            sl = [((host.lm_head if layer < 0 else host.layers[layer][p[0]]), p[3], p[4]) for p in grp]
+        if fmt == "AWQ":
+            gs = sl[0][0].data[3]
+            qw = np.concatenate([hp.data[0][:, r0 // 8:(r0 + nr) // 8] for hp, r0, nr in sl], axis=1)
+            sc = np.concatenate([hp.data[1][:, r0:r0 + nr] for hp, r0, nr in sl], axis=1)
+            zr = np.concatenate([hp.data[2][:, r0:r0 + nr] for hp, r0, nr in sl], axis=1)
+            dq = ops.DecomposedQuantTensor(np.ascontiguousarray(qw), np.ascontiguousarray(sc), np.ascontiguousarray(zr), None,
+                                           ops.DecomposedQuantMethod("awq", gs), (nrows, K))
+            return self.c.weight_from_decomposed(dq, cols=(k0, k1) if kslice is not None else None)
+        if fmt == "GPTQ":
+            gs = sl[0][0].data[4]
+            qw = np.concatenate([hp.data[0][:, r0:r0 + nr] for hp, r0, nr in sl], axis=1)
+            sc = np.concatenate([hp.data[1][:, r0:r0 + nr] for hp, r0, nr in sl], axis=1)
+            qz = np.concatenate([hp.data[2][:, r0 // 8:(r0 + nr) // 8] for hp, r0, nr in sl], axis=1)
+            if kslice is not None:  # K shard: slice the source tensors (groups are contiguous: no act-order here)
+                qw, sc, qz = qw[k0 // 8:k1 // 8], sc[k0 // gs:k1 // gs], qz[k0 // gs:k1 // gs]
+            dq = ops.DecomposedQuantTensor(np.ascontiguousarray(qw), np.ascontiguousarray(sc), np.ascontiguousarray(qz), None,
+                                           ops.DecomposedQuantMethod("gptq", gs), (nrows, k1 - k0))
+            return self.c.weight_from_decomposed(dq)
+        raise ValueError(fmt)
+
+    # ---- one decode step ------------------------------------------------------------------------------
+    def _matvec(self, lins: List[_Linear], xq: torch.Tensor, out: torch.Tensor):
+        L = ops.lib()
+        st = ops._stream_ptr(self.dev)
+        for ln in lins:
+            ops._check(L.b200q_matmul_q8(ln.w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(self.M),
+                                         C.c_void_p(out.data_ptr() + 4 * ln.col0), C.c_int32(ops.F32), C.c_int64(out.stride(0)),
+                                         C.c_void_p(ln.ws.data_ptr()), C.c_size_t(ln.ws.numel()), st))
+
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.group)
+
+    def step(self):
+        """ids (device) -> next ids (device); positions advance on the device: graph-replayable."""
+        L, cfg, M = ops.lib(), self.cfg, self.M
+        st = ops._stream_ptr(self.dev)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        ops._check(L.b200q_embed(P(self.embed), P(self.ids), C.c_int64(cfg.hidden), C.c_int64(M), P(self.h), st))
+        delta = None
+        for lay in self.layers:
+            ops._check(L.b200q_add_rmsnorm_quant(P(self.h), P(delta) if delta is not None else None, P(lay["attn_norm"]), C.c_float(cfg.eps),
+                                                 C.c_int64(cfg.hidden), C.c_int64(M), P(self.xq_h), None, st))
+            self._matvec(lay["qkv"], self.xq_h, self.qkv)
+            ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
+                                           C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
+                                           P(self.xq_attn), None, st))
+            self._matvec(lay["o"], self.xq_attn, self.delta)
+            self._allreduce(self.delta)
+            ops._check(L.b200q_add_rmsnorm_quant(P(self.h), P(self.delta), P(lay["mlp_norm"]), C.c_float(cfg.eps), C.c_int64(cfg.hidden),
+                                                 C.c_int64(M), P(self.xq_h), None, st))
+            self._matvec(lay["gu"], self.xq_h, self.gu)
+            ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
+            self._matvec(lay["down"], self.xq_ff, self.delta)
+            self._allreduce(self.delta)
+            delta = self.delta
+        ops._check(L.b200q_add_rmsnorm_quant(P(self.h), P(delta), P(self.final_norm), C.c_float(cfg.eps), C.c_int64(cfg.hidden), C.c_int64(M),
+                                             P(self.xq_h), None, st))
+        self._matvec(self.head, self.xq_h, self.logits_local)
+        if self.world > 1:
+            torch.distributed.all_gather_into_tensor(self.logits, self.logits_local, group=self.group)
+            full = self.logits.permute(1, 0, 2).reshape(M, -1).contiguous()  # ranks hold consecutive vocab slices
+            ops._check(L.b200q_argmax(P(full), C.c_int64(full.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
+            self._full_logits = full
+        else:
+            ops._check(L.b200q_argmax(P(self.logits), C.c_int64(self.logits.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
+
+    def launches_per_step(self) -> int:
+        n = 1 + 1 + len(self.head) + 1  # embed, final norm, head, argmax
+        for lay in self.layers:
+            n += 2 + len(lay["qkv"]) + 1 + len(lay["o"]) + len(lay["gu"]) + 1 + len(lay["down"])
+        return n
+
+    def capture(self):
+        """capture one decode step into a CUDA graph (reference src/engine/cuda_graphs.rs:124-130)"""
+        self.step()  # un-captured warm-up forward (cuda_graphs.rs:104)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                self.step()
+        torch.cuda.synchronize(self.dev)
+        self.graph = g
+        return g
+
+    def reset(self, first_ids):
+        self.ids.copy_(torch.as_tensor(first_ids, dtype=torch.int64, device=self.dev).reshape(self.M))
+        self.pos.zero_()
+
+    def generate(self, prompt: np.ndarray, n_new: int, use_graph: bool = True) -> np.ndarray:
+        """prompt: int64 [M, S].  Greedy: feeds the prompt token by token (decode steps), then n_new tokens."""
+        prompt = np.asarray(prompt, dtype=np.int64).reshape(self.M, -1)
+        S = prompt.shape[1]
+        if use_graph and self.graph is None:
+            self.capture()
+        self.reset(prompt[:, 0])
+        run = (lambda: self.graph.replay()) if use_graph else self.step
+        out = []
+        for s_ in range(S + n_new - 1):
+            run()
+            if s_ + 1 < S:
+                self.ids.copy_(torch.from_numpy(prompt[:, s_ + 1]).to(self.dev))  # teacher-force the prompt
+            else:
+                out.append(self.ids.clone())
+        torch.cuda.synchronize(self.dev)
+        return torch.stack(out, dim=1).cpu().numpy()

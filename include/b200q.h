@@ -150,6 +150,26 @@ int32_t b200q_dequantize(const b200q_weight* w, void* out, int32_t dtype, void* 
 int32_t b200q_act_unpack(const void* xq, int64_t M, int64_t K, int8_t* q, float* d, int32_t* bsum16, void* stream);
 int32_t b200q_int_partials(const b200q_weight* w, const void* xq, int64_t M, int32_t* partials, void* stream);
 
+
+/* ---- decode-step glue operators (outside the quantized-matmul path; SURVEY.md section 8f "next") ----
+ * They let one whole decode step be captured in a CUDA graph: each emits the int8 activation records
+ * (b200q_act_bytes layout) that the following b200q_matmul_q8 consumes, so no separate quantise pass runs.
+ * Reference call sites: src/engine/cuda_graphs.rs:101-130 (captured forward + argmax_to_buf). */
+/* h[M,H] += delta (nullable); xq = quant(rmsnorm(h) * w); xnorm (nullable) receives the f32 normalised row */
+int32_t b200q_add_rmsnorm_quant(float* h, const float* delta, const float* w, float eps, int64_t H, int64_t M, void* xq, float* xnorm,
+                                void* stream);
+/* xq = quant(silu(gate) * up) for gate_up[M, 2F] (gate first) */
+int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream);
+/* RoPE (adjacent pairs; cos/sin from rope_table [max_ctx][hd/2][2] f32) on q and the new k, KV append at pos[m],
+ * single-query attention (f64 reductions, deterministic exp), quantised output.
+ * qkv[M,(nh+2nkv)*hd] f32; caches [M][max_ctx][nkv][hd] f32; attn_out (nullable) receives the f32 result */
+int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table, int32_t n_heads,
+                          int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq, float* attn_out, void* stream);
+/* greedy token: argmax over V, lowest index wins ties; pos_inc (nullable) is incremented per row (graph replay) */
+int32_t b200q_argmax(const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream);
+/* h[m,:] = f16 table[ids[m],:] */
+int32_t b200q_embed(const void* table_f16, const int64_t* ids, int64_t H, int64_t M, float* h, void* stream);
+
 /* number of kernels the library has launched on this process (all threads); for bench accounting */
 int64_t b200q_launch_count(void);
 

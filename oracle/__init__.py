@@ -237,3 +237,11 @@ def shard_range(total: int, rank: int, world: int):
     s, e = C.c_int64(), C.c_int64()
     lib().orc_shard_range(C.c_int64(total), C.c_int64(rank), C.c_int64(world), C.byref(s), C.byref(e))
     return int(s.value), int(e.value)
+
+
+def det_exp(x: np.ndarray) -> np.ndarray:
+    """deterministic f32 exp shared bit-for-bit with the GPU glue kernels (common.cuh det_expf)"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    lib().orc_det_expf(_p(x), C.c_int64(x.size), _p(out))
+    return out

@@ -337,7 +337,7 @@ void orc_matmul_ggml_f32(int t, const uint8_t* blocks, int64_t N, int64_t K, con
 /*
  * flavour B from the decomposition: int8 activations (orc_quantize_act), integer dot per sub-block,
  *   Y[m,n] = sum_p (a_p * dx_blk(p)) * partial_p  -  sum_p (b_p * dx_blk(p)) * bsum_p   (+bias)
- * accumulated in double.
+ * accumulated in double (exact products, see below): bit-exact contract #3 for the dp4a decode path.
  */
 void orc_matmul_q8(const int8_t* qi, const float* a, const float* b, int sub, int64_t N, int64_t K,
                    const int8_t* xq, const float* xd, const int32_t* xbsum16, int64_t M, const float* bias, float* Y) {
@@ -355,7 +355,10 @@ void orc_matmul_q8(const int8_t* qi, const float* a, const float* b, int sub, in
                 int32_t bs;
                 if (sub == 32) bs = xbsum16[(m * (K / 32) + blk) * 2] + xbsum16[(m * (K / 32) + blk) * 2 + 1];
                 else bs = xbsum16[m * (K / 16) + p];
-                acc += (double)(a[n * P + p] * dx) * (double)s - (double)(b[n * P + p] * dx) * (double)bs;
+                /* each product is exact in f64 (24-bit x <=24-bit), so the f64 sum is order independent to 1e-16:
+                 * the GPU kernel forms the very same terms and is bit-comparable after the final f32 rounding */
+                acc += (double)(a[n * P + p] * dx) * (double)s;
+                acc -= (double)(b[n * P + p] * dx) * (double)bs;
             }
             if (bias) acc += (double)bias[n];
             Y[m * N + n] = (float)acc;
@@ -505,3 +508,25 @@ void orc_shard_range(int64_t total, int64_t rank, int64_t world, int64_t* start,
 
 /* f32 <-> bf16/f16 helpers so tests can build inputs identically to the device path */
 float orc_h2f(uint16_t h) { return h2f(h); }
+
+/* Deterministic expf, line-for-line the same IEEE operations as blazr_b200/csrc/common.cuh det_expf
+ * (fmaf is correctly rounded on both sides; compile with -mfma so it is one instruction). */
+static float det_expf(float x) {
+    x = fminf(fmaxf(x, -87.0f), 88.0f);
+    const float n = rintf(x * 1.44269504f);
+    float r = fmaf(n, -0.693145752f, x);
+    r = fmaf(n, -1.42860677e-6f, r);
+    float p = 1.0f / 720.0f;
+    p = fmaf(p, r, 1.0f / 120.0f);
+    p = fmaf(p, r, 1.0f / 24.0f);
+    p = fmaf(p, r, 1.0f / 6.0f);
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    union { uint32_t u; float f; } sc;
+    sc.u = (uint32_t)(((int)n + 127) << 23);
+    return p * sc.f;
+}
+void orc_det_expf(const float* x, int64_t n, float* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = det_expf(x[i]);
+}

@@ -20,11 +20,20 @@ pytestmark = pytest.mark.gpu
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ggml_dequant.npz"))
 TOL_A = 1e-2   # north_star: 1e-2 relative on outputs vs the reference CPU (f32) path
-TOL_B = 2e-4   # same int8 arithmetic, only the f32 summation order differs
+TOL_B = 1e-6   # same int8 arithmetic with exact f64 accumulation on both sides: bit-identical up to rare 1-ulp cases
 
 
 def rel_err(y, ref):
     return float(np.abs(y.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def assert_bit_exact(y, ref, what=""):
+    """contract #3 (decode path): the f32 outputs equal the oracle's bit for bit; a double-rounding
+    coincidence (f64 sum within 1e-16 of an f32 midpoint) may flip the last bit of < 1e-4 of the elements"""
+    y, ref = np.asarray(y, dtype=np.float32), np.asarray(ref, dtype=np.float32)
+    neq = y.view(np.uint32) != ref.view(np.uint32)
+    assert neq.mean() < 1e-4, (what, float(neq.mean()))
+    assert rel_err(y, ref) < TOL_B, what
 
 
 def test_native_library_is_loaded(client):
@@ -136,7 +145,7 @@ def test_matvec_m1_vs_oracle(client, fmt, shape):
     x = synth.random_act(1, K, seed=5)
     y = client.quant_matmul(torch.from_numpy(x).cuda(), c.w, path=ops.PATH_MATVEC).cpu().numpy()
     assert y.shape == (1, N)
-    assert rel_err(y, c.oracle_b(x)) < TOL_B
+    assert_bit_exact(y, c.oracle_b(x), (fmt, shape))
     assert rel_err(y, c.oracle_a(x)) < TOL_A
 
 
@@ -147,7 +156,7 @@ def test_matvec_small_batch(client, fmt, M):
     c = Case(client, fmt, N, K, seed=M)
     x = synth.random_act(M, K, seed=6)
     y = client.quant_matmul(torch.from_numpy(x).cuda(), c.w, path=ops.PATH_MATVEC).cpu().numpy()
-    assert rel_err(y, c.oracle_b(x)) < TOL_B
+    assert_bit_exact(y, c.oracle_b(x), (fmt, M))
     assert rel_err(y, c.oracle_a(x)) < TOL_A
 
 
