@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of the quantized linear-layer hot path on B200 (BASELINE.json metric).
+
+A *step* is one decode token of the named random-init model: every quantized projection of the model
+(4 fused matvec launches per layer + lm_head; 7L+1 projections) plus the glue operators, replayed from one
+CUDA graph (the caller pattern of reference src/engine/cuda_graphs.rs:166-189).
+
+    python bench.py --gpus 1 --steps 128 --warmup 16                 # Mistral-7B GGUF Q6_K, batch-1 decode
+    torchrun ... bench.py --gpus N ...                               # same model, tensor-parallel over N GPUs
+    python bench.py --impl reference ...                             # the CPU path (oracle port) on host cores
+
+JSON line (one, from rank 0): value = tokens/s with inputs resident in HBM (graph replay, device timed);
+e2e = tokens/s through the public step API with the token id coming from / going to pinned host memory every
+step (what blazr's decode loop does: one upload, one 8-byte D2H per token, executor_generate.rs:362-405);
+roofline = the dominant kernel (gate|up matvec) against MEASURED_PEAKS.json; cpu_baseline = the oracle's
+packed-block int8 path on the host cores (reported only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mistral-7b:Q6_K", help="<model preset>:<scheme>  e.g. llama-3-70b:Q4_K_M, llama-3-8b:AWQ")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--prompt", type=int, default=32, help="prompt tokens fed before the timed region (reference bench.rs:24)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (prefill GEMM, batch-32)")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's packed-block int8 path (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_tokens_per_s(model: str, scheme: str, batch: int, budget_s: float = 12.0):
+    """Times the CPU port on a bounded sample of the workload: whole layers (all 7 projections, M = batch)
+    until ~budget_s of work, then scales to 7L+1 projections.  Returns (tok/s, cores, sample text)."""
+    import numpy as np
+
+    import oracle
+    from blazr_b200 import decode, synth
+
+    cfg = decode.PRESETS[model]
+    cores = os.cpu_count() or 1
+    fm = decode.layer_formats(cfg, scheme, cfg.n_layers // 2)
+    qd, kvd = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+    shapes = dict(q=(qd, cfg.hidden), k=(kvd, cfg.hidden), v=(kvd, cfg.hidden), o=(cfg.hidden, qd), gate=(cfg.ffn, cfg.hidden),
+                  up=(cfg.ffn, cfg.hidden), down=(cfg.hidden, cfg.ffn))
+    ggml_like = {p: (f if f in synth.GGML else "Q4_0") for p, f in fm.items()}  # INT4 group formats: timed as a 4-bit block format
+    lin = []
+    for p, (N, K) in shapes.items():
+        t = synth.GGML[ggml_like[p]]
+        lin.append((t, N, K, synth.random_ggml(t, N, K, seed=1)))
+    xs = {K: oracle.quantize_act(synth.random_act(batch, K)) for K in {s[1] for s in shapes.values()}}
+    params_layer = sum(N * K for _, N, K, _ in lin)
+    # warm-up + timed repetitions of one layer
+    for t, N, K, blk in lin[:2]:
+        oracle.matvec_ggml_q8(t, blk, N, K, *xs[K])
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        for t, N, K, blk in lin:
+            oracle.matvec_ggml_q8(t, blk, N, K, *xs[K])
+        reps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    t_layer = (time.perf_counter() - t0) / reps
+    params_total = params_layer * cfg.n_layers + cfg.vocab * cfg.hidden
+    t_token = t_layer * params_total / params_layer
+    sample = (f"{reps} x one layer ({params_layer / 1e6:.0f}M weights, 7 projections, M={batch}) of {model} {scheme} through the oracle's "
+              f"packed-block int8 matvec, OpenMP over rows; scaled by weights to 7L+1 projections")
+    return batch / t_token, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, scheme = args.workload.split(":")
+    toks, cores, sample = cpu_tokens_per_s(model, scheme, args.batch, budget_s=20.0)
+    out = {
+        "metric": "decode_tokens_per_s", "value": toks, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.batch / toks, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4/6/8 -> f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"{model} GGUF {scheme} random-init, batch-{args.batch} greedy decode (CPU path)", "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": toks, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": toks, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    from blazr_b200 import decode, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    model, scheme = args.workload.split(":")
+    cfg = decode.PRESETS[model]
+    client = ops.B200Client(local)
+    M = args.batch
+    max_ctx = args.prompt + args.warmup + 2 * args.steps + 64
+    launches0 = ops.launch_count()
+    dec = decode.Decoder(client, cfg, scheme, batch=M, max_ctx=max_ctx, tp_rank=rank, tp_world=world)
+    if world > 1:
+        dist.barrier()
+    dec.capture()
+    g = dec.graph
+    dev = client.device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    rng = np.random.Generator(np.random.PCG64(11))
+    prompt = rng.integers(0, cfg.vocab, size=(M, args.prompt))
+    dec.reset(prompt[:, 0])
+    for s in range(args.prompt - 1):  # feed the prompt through decode steps (keeps the KV cache realistic)
+        g.replay()
+        dec.ids.copy_(torch.from_numpy(prompt[:, s + 1]).to(dev))
+    for _ in range(max(3, args.warmup)):
+        g.replay()
+
+    # ---- device-resident throughput: K graph replays between events ----
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        g.replay()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the step API with host buffers ----
+    pin_in = torch.zeros(M, dtype=torch.int64).pin_memory()
+    pin_out = torch.zeros(M, dtype=torch.int64).pin_memory()
+    pin_in.copy_(dec.ids.cpu())
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        dec.ids.copy_(pin_in, non_blocking=True)   # H2D: this step's input token ids
+        g.replay()
+        pin_out.copy_(dec.ids, non_blocking=True)  # D2H: the sampled token ids
+        torch.cuda.current_stream().synchronize()  # the host needs the token before it can issue the next step
+        pin_in.copy_(pin_out)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel: the fused gate|up matvec, timed alone over all layers ----
+    pk, pk_kind = peaks()
+    gu = [lay["gu"][0] for lay in dec.layers]
+    reps = 20
+
+    def run_gu():
+        for ln in gu:
+            dec._matvec([ln], dec.xq_h, dec.gu)
+
+    run_gu()
+    torch.cuda.synchronize(dev)
+    g2 = torch.cuda.CUDAGraph()
+    s2 = torch.cuda.Stream(dev)
+    s2.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s2):
+        with torch.cuda.graph(g2, stream=s2):
+            run_gu()
+        for _ in range(3):
+            g2.replay()
+        s2.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(s2)
+        for _ in range(reps):
+            g2.replay()
+        k1.record(s2)
+        s2.synchronize()
+    us_gu = k0.elapsed_time(k1) * 1e3 / (reps * len(gu))
+    w0 = gu[0].w
+    bytes_gu = w0.canonical_bytes + M * w0.K * 1.25 + M * w0.N * 4  # canonical packed weights + int8 activation records + f32 outputs
+    achieved = bytes_gu / (us_gu * 1e-6) / 1e9
+    # whole-step view: all matvec weight bytes over the step time
+    step_bytes = dec.weight_bytes
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+            "kernel": f"matvec_kernel<{decode.layer_formats(cfg, scheme, 0)['gate']},{M}> gate|up N={w0.N} K={w0.K}", "us_per_launch": us_gu,
+            "algorithmic_bytes_per_launch": bytes_gu, "peak_kind": pk_kind + " burst (kernel timed alone)",
+            "step_weight_bytes": step_bytes, "step_GBs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+            "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"]}
+
+    extra = {}
+    if not args.no_extra and rank == 0 and world == 1:
+        extra = extras(client, cfg, scheme, pk)
+
+    if rank == 0:
+        toks = M * args.steps / (ms * 1e-3)
+        toks_e2e = M * args.steps / (ms_e2e * 1e-3)
+        cpu_v, cores, sample = cpu_tokens_per_s(model, scheme, M, budget_s=12.0) if world == 1 else (None, None, None)
+        out = {
+            "metric": "decode_tokens_per_s", "value": toks, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int8 activations x int4/6/8 weights, f64-exact accumulate -> f32", "data": "synthetic",
+            "config": {"workload": f"{model} GGUF {scheme} random-init, batch-{M} greedy decode, {args.prompt}-token prompt then {args.steps} tokens",
+                       "parallelism": f"tp{world}", "l2": f"weights {step_bytes * world / 1e9:.1f} GB streamed once per token (>> 126 MB L2)",
+                       "launches_per_step": dec.launches_per_step()},
+            "clocks": clocks,
+            "e2e": {"value": toks_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8 * M, "d2h_bytes_per_step": 8 * M},
+            "gpu_launches": dec.launches_per_step() * args.steps,
+            "roofline": roof,
+            "impl": "b200",
+        }
+        if cpu_v is not None:
+            out["cpu_baseline"] = {"value": cpu_v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+        if extra:
+            out["extra"] = extra
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(client, cfg, scheme, pk):
+    """secondary numbers of the north_star: prefill dequant-GEMM TFLOP/s and batch-32 decode through the
+    tcgen05 path on one projection shape (kernel level)."""
+    import torch
+
+    from blazr_b200 import decode, ops, synth
+
+    out = {}
+    fmt = decode.layer_formats(cfg, scheme, 0)["gate"]
+    if fmt not in synth.GGML:
+        return out
+    N, K = cfg.ffn, cfg.hidden
+    t = synth.GGML[fmt]
+    copies = 4
+    ws = [client.weight_from_ggml(t, decode.random_ggml_device(fmt, N, K, 100 + i, client.device), N, K) for i in range(copies)]
+    for name, Mx in (("prefill_2048", 2048), ("decode_batch32", 32)):
+        x = torch.randn((Mx, K), device=client.device)
+        y = torch.empty((Mx, N), device=client.device)
+        wss = [w.workspace(Mx) for w in ws]
+        for w, s in zip(ws, wss):
+            client.quant_matmul(x, w, out=y, workspace=s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            for w, s in zip(ws, wss):
+                client.quant_matmul(x, w, out=y, workspace=s)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * copies)
+        tf = 2.0 * Mx * N * K / (us * 1e-6) / 1e12
+        out[name] = {"shape": f"{fmt} N={N} K={K} M={Mx}", "us": us, "TFLOPs": tf, "frac_bf16_burst": tf / pk["bf16_tflops"],
+                     "GBs": ws[0].canonical_bytes / (us * 1e-6) / 1e9, "includes": "f16 activation staging kernel + tcgen05 GEMM"}
+    for w in ws:
+        w.free()
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,21 +47,34 @@ static cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size
 }
 
 // ------------------------------------------------------------------------------------------------
-// h (+= delta) ; xq = quant(rmsnorm(h) * w)          one CTA of 256 threads per token row
+// h_out = h_in (+ delta) ; xq = quant(rmsnorm(h_out) * w)
+// One CTA of 256 threads per (256-k chunk, token row): every CTA recomputes the row's sum of squares (the row
+// is 8-32 KB and L2 resident) and then normalises / quantises / writes only its own chunk, so the operator
+// runs H/256 CTAs wide instead of one.  h_in and h_out must be different buffers when delta != null.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(float* __restrict__ h, const float* __restrict__ delta, const float* __restrict__ w,
-                                                                 float eps, int H, int M, uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
+__global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(const float* __restrict__ h_in, const float* __restrict__ delta,
+                                                                 float* __restrict__ h_out, const float* __restrict__ w, float eps, int H, int M,
+                                                                 uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
     pdl_launch_dependents();
     pdl_wait();
-    const int m = blockIdx.x, t = threadIdx.x;
-    float* hr = h + (size_t)m * H;
+    const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
+    const float* hr = h_in + (size_t)m * H;
+    const float* dr = delta ? delta + (size_t)m * H : nullptr;
     __shared__ double red[8];
-    double ss = 0.0;  // f64: exact squares, order-independent sum -> bit-reproducible against the oracle
-    for (int k = t; k < H; k += 256) {
-        float v = hr[k];
-        if (delta) { v = __fadd_rn(v, delta[(size_t)m * H + k]); hr[k] = v; }
-        ss = fma((double)v, (double)v, ss);
+    // f64: exact squares, order-independent sum -> bit-reproducible against the oracle (4 independent chains)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int k4 = t; k4 < H / 4; k4 += 256) {
+        float4 v = reinterpret_cast<const float4*>(hr)[k4];
+        if (dr) {
+            const float4 d4 = reinterpret_cast<const float4*>(dr)[k4];
+            v.x = __fadd_rn(v.x, d4.x); v.y = __fadd_rn(v.y, d4.y); v.z = __fadd_rn(v.z, d4.z); v.w = __fadd_rn(v.w, d4.w);
+        }
+        s0 = fma((double)v.x, (double)v.x, s0); s1 = fma((double)v.y, (double)v.y, s1);
+        s2 = fma((double)v.z, (double)v.z, s2); s3 = fma((double)v.w, (double)v.w, s3);
     }
+    double ss = (s0 + s1) + (s2 + s3);
+    float mine = hr[kc * CHUNK_K + t];
+    if (dr) mine = __fadd_rn(mine, dr[kc * CHUNK_K + t]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((t & 31) == 0) red[t >> 5] = ss;
@@ -70,13 +83,11 @@ __global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(float* __restric
 #pragma unroll
     for (int i = 0; i < 8; i++) tot += red[i];
     const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)H), eps)));
-    const int KCn = H / CHUNK_K;
-    for (int kc = 0; kc < KCn; kc++) {
-        const int k = kc * CHUNK_K + t;
-        const float v = __fmul_rn(__fmul_rn(hr[k], inv), w[k]);
-        if (xnorm) xnorm[(size_t)m * H + k] = v;
-        quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
-    }
+    const int k = kc * CHUNK_K + t;
+    h_out[(size_t)m * H + k] = mine;
+    const float v = __fmul_rn(__fmul_rn(mine, inv), w[k]);
+    if (xnorm) xnorm[(size_t)m * H + k] = v;
+    quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -106,7 +117,6 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float s_sc[];  // scores, then probabilities, for positions 0..p
-    constexpr int EPL = HD / 32;
     const int head = blockIdx.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int kvh = head / (nh / nkv);
     const int p = pos[m];
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     const size_t pstride = (size_t)nkv * HD;
     const float* rt = rope + (size_t)p * HD;  // [hd/2][2]
 
-    __shared__ float sq[HD], sk[HD], sv[HD];
+    __shared__ __align__(16) float sq[HD], sk[HD], sv[HD];
     __shared__ float s_redf[4];
     __shared__ double s_redd[4];
     if (t < HD / 2) {
@@ -137,23 +147,37 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
         }
     }
     __syncthreads();
-    // ---- pass 1: scores ----
+    // ---- pass 1: scores; 4 threads per position (a quarter of the head each), 32 positions per sweep ----
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
     float lmax = -INFINITY;
-    for (int j = warp; j <= p; j += 4) {
-        double d = 0.0;
+    {
+        constexpr int QE = HD / 4;  // elements per thread
+        const int part = t & 3;
+        for (int j0 = 0; j0 <= p; j0 += 32) {
+            const int j = j0 + (t >> 2);
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            if (j <= p) {
+                const float* kr = (j < p) ? ck + (size_t)j * pstride + part * QE : sk + part * QE;  // the new key comes from smem
+                const float* qq = sq + part * QE;
 #pragma unroll
-        for (int e = 0; e < EPL; e++) {
-            const int idx = lane * EPL + e;
-            const float kk = (j < p) ? ck[(size_t)j * pstride + idx] : sk[idx];  // the new key comes from smem: no wait on the appending CTA
-            d = fma((double)sq[idx], (double)kk, d);
+                for (int e = 0; e < QE; e += 4) {
+                    const float4 kk = *reinterpret_cast<const float4*>(kr + e);
+                    d0 = fma((double)qq[e + 0], (double)kk.x, d0); d1 = fma((double)qq[e + 1], (double)kk.y, d1);
+                    d2 = fma((double)qq[e + 2], (double)kk.z, d2); d3 = fma((double)qq[e + 3], (double)kk.w, d3);
+                }
+            }
+            double d = (d0 + d1) + (d2 + d3);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (j <= p) {
+                const float sc = __fmul_rn((float)d, scale);
+                if (part == 0) s_sc[j] = sc;
+                lmax = fmaxf(lmax, sc);
+            }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-        const float sc = __fmul_rn((float)d, scale);
-        if (lane == 0) s_sc[j] = sc;
-        lmax = fmaxf(lmax, sc);
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
     if (lane == 0) s_redf[warp] = lmax;
     __syncthreads();
     const float gmax = fmaxf(fmaxf(s_redf[0], s_redf[1]), fmaxf(s_redf[2], s_redf[3]));
@@ -168,12 +192,29 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     if (lane == 0) s_redd[warp] = lsum;
     __syncthreads();
     const float den = (float)(s_redd[0] + s_redd[1] + s_redd[2] + s_redd[3]);
-    // ---- pass 2: thread t owns output element t ----
+    // ---- pass 2: thread (eg, jg) accumulates 4 output elements over every 4th position; combine through smem ----
+    __shared__ double s_o[4][HD];
+    {
+        constexpr int EG = HD / 4;          // element groups of 4
+        constexpr int JG = 128 / EG;        // position groups (4 for hd 128, 8 for hd 64)
+        const int eg = t % EG, jg = t / EG;
+        double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+        for (int j = jg; j <= p; j += JG) {
+            const float pj = s_sc[j];
+            const float4 vv = (j < p) ? *reinterpret_cast<const float4*>(cv + (size_t)j * pstride + 4 * eg) : *reinterpret_cast<const float4*>(sv + 4 * eg);
+            o0 = fma((double)pj, (double)vv.x, o0); o1 = fma((double)pj, (double)vv.y, o1);
+            o2 = fma((double)pj, (double)vv.z, o2); o3 = fma((double)pj, (double)vv.w, o3);
+        }
+        if (jg < 4) { s_o[jg][4 * eg + 0] = o0; s_o[jg][4 * eg + 1] = o1; s_o[jg][4 * eg + 2] = o2; s_o[jg][4 * eg + 3] = o3; }
+        __syncthreads();
+        if (JG == 8) {  // hd 64: fold the upper four position groups in
+            if (jg >= 4) { s_o[jg - 4][4 * eg + 0] += o0; s_o[jg - 4][4 * eg + 1] += o1; s_o[jg - 4][4 * eg + 2] += o2; s_o[jg - 4][4 * eg + 3] += o3; }
+            __syncthreads();
+        }
+    }
     float outv = 0.0f;
     if (t < HD) {
-        double o = 0.0;
-        for (int j = 0; j < p; j++) o = fma((double)s_sc[j], (double)cv[(size_t)j * pstride + t], o);
-        o = fma((double)s_sc[p], (double)sv[t], o);
+        const double o = (s_o[0][t] + s_o[1][t]) + (s_o[2][t] + s_o[3][t]);
         outv = __fdiv_rn((float)o, den);
         if (attn_out) attn_out[(size_t)m * nh * HD + (size_t)head * HD + t] = outv;
         // quantise this head's HD outputs into the o_proj activation records (32-blocks never straddle heads)
@@ -251,10 +292,12 @@ using namespace b200q;
 
 extern "C" {
 
-int32_t b200q_add_rmsnorm_quant(float* h, const float* delta, const float* w, float eps, int64_t H, int64_t M, void* xq, float* xnorm, void* stream) {
-    if (!h || !w || !xq || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
-    cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)M), dim3(256), 0, (cudaStream_t)stream, h, delta, w, eps, (int)H, (int)M,
-                               (uint8_t*)xq, xnorm);
+int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_out, const float* w, float eps, int64_t H, int64_t M, void* xq,
+                                float* xnorm, void* stream) {
+    if (!h_in || !h_out || !w || !xq || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
+    if (delta && h_in == h_out) return B200Q_ERR_INVALID_ARG;  // CTAs re-read the whole input row: no in-place update
+    cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)(H / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, h_in, delta,
+                               h_out, w, eps, (int)H, (int)M, (uint8_t*)xq, xnorm);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }
 

@@ -81,7 +81,12 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t G = gridDim.x, g = blockIdx.x;
-    if (p.trace && tid == 0) p.trace[g * 8 + 0] = globaltimer_ns();
+    if (p.trace && tid == 0) {
+        p.trace[g * 8 + 0] = globaltimer_ns();
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[g * 8 + 2] = smid;
+    }
     const int64_t c0 = sk_begin(g, p.C, G), c1 = sk_begin(g + 1, p.C, G);
     const int n_chunks = (int)(c1 - c0);
     const int KC = (int)p.KC;
@@ -328,6 +333,29 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// L2 prefetch of the chunks a following matvec launch will stream first.  The matvec CTAs own a whole SM, so
+// the next launch cannot be co-resident; instead this tiny kernel (PDL: starts as soon as the running matvec
+// releases SMs, never waits) asks the TMA engine to pull the first `nchunks` chunks of every CTA's range
+// -- in that CTA's processing order -- into L2 while the glue operators between the two matvecs run.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) l2_prefetch_kernel(const uint8_t* __restrict__ w, int64_t KC, int64_t C, int chunk_bytes, int first, int nchunks) {
+    pdl_launch_dependents();
+    if (threadIdx.x != 0) return;
+    const int64_t G = gridDim.x, g = blockIdx.x;
+    const int64_t c0 = sk_begin(g, C, G), c1 = sk_begin(g + 1, C, G);
+    const SkPlan sp = sk_plan(c0, c1, KC);
+    const int n = (int)(c1 - c0);
+    const uint8_t* base = w + c0 * (int64_t)chunk_bytes;
+    for (int j = first; j < n && j < first + nchunks; j++) {
+        const uint8_t* src;
+        if (j < sp.nH) src = base + (size_t)j * chunk_bytes;
+        else if (j < sp.nH + sp.nT) src = base + (size_t)(sp.nH + sp.nF + (j - sp.nH)) * chunk_bytes;
+        else src = base + (size_t)(sp.nH + (j - sp.nH - sp.nT)) * chunk_bytes;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(chunk_bytes) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <class F, int MB>
@@ -336,7 +364,7 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -375,7 +403,12 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan) {
     int mb = M == 1 ? 1 : (M == 2 ? 2 : 4);
     int stage = w->chunk_bytes + (int)M * ACT_REC_BYTES;
     stage = (stage + 127) & ~127;
-    int budget = 110 * 1024 - MV_HDR_BYTES;  // half an SM: the next kernel's CTA co-resides and prefetches (PDL)
+    // > half an SM on purpose: two CTAs of one launch must never share an SM (measured: after glue kernels perturb
+    // the placement, doubled-up CTAs run at half speed and the launch takes 2x); cross-launch overlap is done
+    // with the L2 prefetch kernel instead
+    int budget_kb = 150;
+    if (const char* e = getenv("B200Q_MV_SMEM_KB")) { int v = atoi(e); if (v >= 64 && v <= 224) budget_kb = v; }
+    int budget = budget_kb * 1024 - MV_HDR_BYTES;
     int nst = budget / stage;
     if (nst > MV_MAX_STAGES) nst = MV_MAX_STAGES;
     if (const char* e = getenv("B200Q_MV_STAGES")) { int v = atoi(e); if (v >= 2 && v < nst) nst = v; }
@@ -441,4 +474,26 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     }
 }
 
+}  // namespace b200q
+
+namespace b200q {
+cudaError_t launch_l2_prefetch(const b200q_weight* w, int64_t M, int64_t max_bytes, cudaStream_t st) {
+    MatvecPlan plan;
+    cudaError_t e = matvec_plan(w, M < 1 ? 1 : (M > 4 ? 4 : M), &plan);
+    if (e != cudaSuccess) return e;
+    int nchunks = (int)(max_bytes / ((int64_t)plan.grid * w->chunk_bytes));
+    if (nchunks < 1) return cudaSuccess;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3(32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, l2_prefetch_kernel, (const uint8_t*)w->data, (int64_t)w->KC, (int64_t)(w->T * w->KC), w->chunk_bytes, 0, nchunks);
+    count_launch();
+    return e;
+}
 }  // namespace b200q

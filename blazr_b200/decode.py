@@ -214,6 +214,7 @@ class Decoder:
         # activations / scratch (all addresses stable: the step is graph-capturable)
         f32 = dict(dtype=torch.float32, device=dev)
         self.h = torch.zeros((M, H), **f32)
+        self.h2 = torch.zeros((M, H), **f32)  # residual stream ping-pong (the fused add+norm is not in-place)
         self.delta = torch.zeros((M, H), **f32)
         self.qkv = torch.zeros((M, self.qd + 2 * self.kvd), **f32)
         self.gu = torch.zeros((M, 2 * self.ff), **f32)
@@ -223,7 +224,8 @@ class Decoder:
         self.pos = torch.zeros(M, dtype=torch.int32, device=dev)
         act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
         self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
-        self.first_step = True
+        import os as _os
+        self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
 
     # ---- weights ------------------------------------------------------------------------------------
@@ -290,6 +292,12 @@ class Decoder:
         raise ValueError(fmt)
 
     # ---- one decode step ------------------------------------------------------------------------------
+    def _prefetch(self, lins: List[_Linear]):
+        """L2 prefetch hint for the matvec that follows the upcoming glue operator"""
+        if self.pf_bytes <= 0:
+            return
+        ops._check(ops.lib().b200q_weight_prefetch_l2(lins[0].w.handle, C.c_int64(self.M), C.c_int64(self.pf_bytes), ops._stream_ptr(self.dev)))
+
     def _matvec(self, lins: List[_Linear], xq: torch.Tensor, out: torch.Tensor):
         L = ops.lib()
         st = ops._stream_ptr(self.dev)
@@ -308,25 +316,34 @@ class Decoder:
         st = ops._stream_ptr(self.dev)
         P = lambda t: C.c_void_p(t.data_ptr())
         ops._check(L.b200q_embed(P(self.embed), P(self.ids), C.c_int64(cfg.hidden), C.c_int64(M), P(self.h), st))
+        hin, hout = self.h, self.h2
         delta = None
-        for lay in self.layers:
-            ops._check(L.b200q_add_rmsnorm_quant(P(self.h), P(delta) if delta is not None else None, P(lay["attn_norm"]), C.c_float(cfg.eps),
+
+        def norm(w):
+            nonlocal hin, hout
+            ops._check(L.b200q_add_rmsnorm_quant(P(hin), P(delta) if delta is not None else None, P(hout), P(w), C.c_float(cfg.eps),
                                                  C.c_int64(cfg.hidden), C.c_int64(M), P(self.xq_h), None, st))
+            hin, hout = hout, hin
+
+        for li, lay in enumerate(self.layers):
+            norm(lay["attn_norm"])
             self._matvec(lay["qkv"], self.xq_h, self.qkv)
+            self._prefetch(lay["o"])
             ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
                                            C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
                                            P(self.xq_attn), None, st))
             self._matvec(lay["o"], self.xq_attn, self.delta)
-            self._allreduce(self.delta)
-            ops._check(L.b200q_add_rmsnorm_quant(P(self.h), P(self.delta), P(lay["mlp_norm"]), C.c_float(cfg.eps), C.c_int64(cfg.hidden),
-                                                 C.c_int64(M), P(self.xq_h), None, st))
-            self._matvec(lay["gu"], self.xq_h, self.gu)
-            ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
-            self._matvec(lay["down"], self.xq_ff, self.delta)
+            self._prefetch(lay["gu"])
             self._allreduce(self.delta)
             delta = self.delta
-        ops._check(L.b200q_add_rmsnorm_quant(P(self.h), P(delta), P(self.final_norm), C.c_float(cfg.eps), C.c_int64(cfg.hidden), C.c_int64(M),
-                                             P(self.xq_h), None, st))
+            norm(lay["mlp_norm"])
+            self._matvec(lay["gu"], self.xq_h, self.gu)
+            self._prefetch(lay["down"])
+            ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
+            self._matvec(lay["down"], self.xq_ff, self.delta)
+            self._prefetch(self.layers[li + 1]["qkv"] if li + 1 < len(self.layers) else self.head)
+            self._allreduce(self.delta)
+        norm(self.final_norm)
         self._matvec(self.head, self.xq_h, self.logits_local)
         if self.world > 1:
             torch.distributed.all_gather_into_tensor(self.logits, self.logits_local, group=self.group)

@@ -139,6 +139,9 @@ int32_t b200q_quantize_act(const void* x, int32_t x_dtype, int64_t M, int64_t K,
                            void* xq, void* stream);
 int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* y, int32_t y_dtype, int64_t ldy,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Hint: ask the TMA engine to pull the first `max_bytes` of w (in the order the next b200q_matmul_q8(w, M) will
+ * stream them) into L2.  Enqueue it right after the preceding matmul: it overlaps the operators in between. */
+int32_t b200q_weight_prefetch_l2(const b200q_weight* w, int64_t M, int64_t max_bytes, void* stream);
 /* Force a path (testing / benchmarking): 0 = auto, 1 = dp4a matvec, 2 = tcgen05 GEMM */
 int32_t b200q_matmul_path(const b200q_weight* w, int32_t path, const void* x, int32_t x_dtype, int64_t M, int64_t ldx, void* y,
                           int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
@@ -155,9 +158,10 @@ int32_t b200q_int_partials(const b200q_weight* w, const void* xq, int64_t M, int
  * They let one whole decode step be captured in a CUDA graph: each emits the int8 activation records
  * (b200q_act_bytes layout) that the following b200q_matmul_q8 consumes, so no separate quantise pass runs.
  * Reference call sites: src/engine/cuda_graphs.rs:101-130 (captured forward + argmax_to_buf). */
-/* h[M,H] += delta (nullable); xq = quant(rmsnorm(h) * w); xnorm (nullable) receives the f32 normalised row */
-int32_t b200q_add_rmsnorm_quant(float* h, const float* delta, const float* w, float eps, int64_t H, int64_t M, void* xq, float* xnorm,
-                                void* stream);
+/* h_out[M,H] = h_in (+ delta, nullable); xq = quant(rmsnorm(h_out) * w); xnorm (nullable) receives the f32 normalised
+ * row.  h_in and h_out must differ when delta != NULL (the operator runs H/256 CTAs wide and re-reads the row). */
+int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_out, const float* w, float eps, int64_t H, int64_t M,
+                                void* xq, float* xnorm, void* stream);
 /* xq = quant(silu(gate) * up) for gate_up[M, 2F] (gate first) */
 int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream);
 /* RoPE (adjacent pairs; cos/sin from rope_table [max_ctx][hd/2][2] f32) on q and the new k, KV append at pos[m],
