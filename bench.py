@@ -290,8 +290,12 @@ def run_b200(args):
             out["extra"] = extra
         print(json.dumps(out), flush=True)
     if world > 1:
+        # NCCL kernels are baked into the captured graphs: drop the graphs, then leave without the collective
+        # teardown (destroy_process_group can block on communicators that captured graphs still reference)
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def extras(client, cfg, scheme, pk):

@@ -24,7 +24,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import ops, synth
+from . import ops, synth, tp
 
 
 @dataclass
@@ -174,12 +174,13 @@ class Decoder:
         dev = client.device
         self.dev = dev
         H, hd = cfg.hidden, cfg.head_dim
-        assert cfg.n_heads % tp_world == 0 and cfg.n_kv_heads % tp_world == 0, "heads must divide tp (tensor_parallel.rs:90-101)"
-        self.nh, self.nkv = cfg.n_heads // tp_world, cfg.n_kv_heads // tp_world
+        pl = tp.plan(H, cfg.n_heads, cfg.n_kv_heads, hd, cfg.ffn, cfg.vocab, tp_rank, tp_world)  # tensor_parallel.rs:61-101
+        self.plan = pl
+        self.nh, self.nkv = pl.n_heads, pl.n_kv_heads
         self.qd, self.kvd = self.nh * hd, self.nkv * hd
-        f0, f1 = ops.shard_range(cfg.ffn, tp_rank, tp_world, granule=256)
+        f0, f1 = pl.ffn_rows
         self.ff = f1 - f0
-        v0, v1 = ops.shard_range(cfg.vocab, tp_rank, tp_world, granule=128)
+        v0, v1 = pl.vocab_rows
         self.v0, self.v1 = v0, v1
         self.weight_bytes = 0
         self.layers = []
@@ -188,11 +189,11 @@ class Decoder:
             fm = layer_formats(cfg, scheme, i)
             lay = {}
             # column-parallel q | k | v (rows of this rank's heads), fused where formats agree
-            lay["qkv"] = self._fused(i, [("q", fm["q"], cfg.n_heads * hd, self.rank * self.qd, self.qd),
-                                         ("k", fm["k"], cfg.n_kv_heads * hd, self.rank * self.kvd, self.kvd),
-                                         ("v", fm["v"], cfg.n_kv_heads * hd, self.rank * self.kvd, self.kvd)], H, host)
+            lay["qkv"] = self._fused(i, [("q", fm["q"], cfg.n_heads * hd, pl.q_rows[0], self.qd),
+                                         ("k", fm["k"], cfg.n_kv_heads * hd, pl.kv_rows[0], self.kvd),
+                                         ("v", fm["v"], cfg.n_kv_heads * hd, pl.kv_rows[0], self.kvd)], H, host)
             # row-parallel o: K slice = this rank's heads
-            lay["o"] = self._fused(i, [("o", fm["o"], H, 0, H)], cfg.n_heads * hd, host, kslice=(self.rank * self.qd, (self.rank + 1) * self.qd))
+            lay["o"] = self._fused(i, [("o", fm["o"], H, 0, H)], cfg.n_heads * hd, host, kslice=pl.o_cols)
             lay["gu"] = self._fused(i, [("gate", fm["gate"], cfg.ffn, f0, self.ff), ("up", fm["up"], cfg.ffn, f0, self.ff)], H, host)
             lay["down"] = self._fused(i, [("down", fm["down"], H, 0, H)], cfg.ffn, host, kslice=(f0, f1))
             an = host.layers[i]["attn_norm"] if host else np.ones(H, np.float32)

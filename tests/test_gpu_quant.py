@@ -264,3 +264,15 @@ def test_errors_are_codes(client):
     sc = sc * np.float32(1.0001)  # no longer f16-representable
     with pytest.raises(ops.B200QError):
         client.weight_from_decomposed(ops.DecomposedQuantTensor(qw, sc, zr, None, ops.DecomposedQuantMethod("awq", 128), (128, 256)))
+
+
+def test_cpp_host_mirror_smoke(client):
+    """the compiled-language host side (blazr_b200/host/b200q.hpp) drives the C ABI end to end"""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(ops.LIB_PATH), "..", "host", "host_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("host_smoke not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host_smoke ok" in r.stdout
