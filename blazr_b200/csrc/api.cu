@@ -407,6 +407,38 @@ int32_t b200q_int_partials(const b200q_weight* w, const void* xq, int64_t M, int
     return B200Q_OK;
 }
 
+static int32_t fused_common(const b200q_weight* w, int64_t M, void* y, int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes) {
+    if (!w || !y || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+    if (M < 1 || M > 4) return fail(B200Q_ERR_UNSUPPORTED, "fused decode matmul handles M in [1,4] (got %lld)", (long long)M);
+    if (ldy < w->N || y_dtype < 0 || y_dtype > 2) return fail(B200Q_ERR_INVALID_ARG, "bad ldy / y_dtype");
+    if (w->perm) return fail(B200Q_ERR_UNSUPPORTED, "act-order (permuted K) weights need the split quantize_act + matmul_q8 path");
+    if (w->K != w->K_pad) return fail(B200Q_ERR_UNSUPPORTED, "fused prologues need K %% 256 == 0");
+    if (workspace_bytes < align256(matvec_ws_bytes(w, M))) return fail(B200Q_ERR_WORKSPACE, "workspace too small");
+    return B200Q_OK;
+}
+
+int32_t b200q_matmul_norm(const b200q_weight* w, const float* h_in, const float* delta, float* h_out, const float* norm_w, float eps, int64_t M,
+                          void* y, int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+    int32_t rc = fused_common(w, M, y, y_dtype, ldy, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!h_in || !norm_w) return fail(B200Q_ERR_INVALID_ARG, "null h_in / norm_w");
+    if (w->K > 8192) return fail(B200Q_ERR_UNSUPPORTED, "fused norm prologue supports K <= 8192");
+    if (delta && h_out == h_in) return fail(B200Q_ERR_INVALID_ARG, "h_out must not alias h_in when delta is given");
+    FusedPrologue fp{1, h_in, delta, h_out, norm_w, eps, nullptr};
+    CUDA_TRY(launch_matvec(w, nullptr, M, y, y_dtype, ldy, (uint8_t*)workspace, (cudaStream_t)stream, &fp));
+    return B200Q_OK;
+}
+
+int32_t b200q_matmul_swiglu(const b200q_weight* w, const float* gate_up, int64_t M, void* y, int32_t y_dtype, int64_t ldy, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    int32_t rc = fused_common(w, M, y, y_dtype, ldy, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!gate_up) return fail(B200Q_ERR_INVALID_ARG, "null gate_up");
+    FusedPrologue fp{2, nullptr, nullptr, nullptr, nullptr, 0.0f, gate_up};
+    CUDA_TRY(launch_matvec(w, nullptr, M, y, y_dtype, ldy, (uint8_t*)workspace, (cudaStream_t)stream, &fp));
+    return B200Q_OK;
+}
+
 int32_t b200q_weight_prefetch_l2(const b200q_weight* w, int64_t M, int64_t max_bytes, void* stream) {
     if (!w || max_bytes < 0) return fail(B200Q_ERR_INVALID_ARG, "bad prefetch arguments");
     CUDA_TRY(launch_l2_prefetch(w, M, max_bytes, (cudaStream_t)stream));

@@ -17,7 +17,8 @@ __device__ __forceinline__ void quant_store_record(float v, uint8_t* rec, int t)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     const float d = __fdiv_rn(amax, 127.0f);
-    const int q = (amax == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v, d));
+    const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+    const int q = (int)roundf(__fmul_rn(v, id));
     int s = q;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
         const float d = __fdiv_rn(amax, 127.0f);
-        const int q = (amax == 0.0f) ? 0 : (int)roundf(__fdiv_rn(outv, d));
+        const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+        const int q = (int)roundf(__fmul_rn(outv, id));
         int s = q;
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);

@@ -71,6 +71,7 @@ __device__ __forceinline__ void store_nib_unit(uint8_t* dst, const uint8_t* q) {
 // ------------------------------------------------------------------------------------------------
 struct FmtQ4K {
     static constexpr int FAMILY = 1, SUB = 32;
+    static constexpr bool SIGNED = false;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = true;
     static constexpr int QS = 0, HDR = 128 * 128;
     __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 144; }
@@ -124,6 +125,7 @@ struct FmtQ4K {
 // ------------------------------------------------------------------------------------------------
 struct FmtQ6K {
     static constexpr int FAMILY = 2, SUB = 16;
+    static constexpr bool SIGNED = false;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = false;
     static constexpr int QL = 0, QH = 128 * 128, SC = QH + 128 * 64, D = SC + 128 * 16;
     __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 210; }
@@ -192,6 +194,7 @@ struct FmtQ6K {
 // ------------------------------------------------------------------------------------------------
 struct FmtQ8_0 {
     static constexpr int FAMILY = 3, SUB = 32;
+    static constexpr bool SIGNED = true;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = false;
     static constexpr int QS = 0, D = 128 * 256;
     __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 272; }
@@ -230,6 +233,7 @@ struct FmtQ8_0 {
 // ------------------------------------------------------------------------------------------------
 struct FmtG4 {
     static constexpr int FAMILY = 4, SUB = 32;
+    static constexpr bool SIGNED = false;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = false;
     static constexpr int QS = 0, SC = 128 * 128;
     __host__ __device__ static constexpr int chunk_bytes(int gpc) { return 128 * 128 + 128 * gpc * 3; }

@@ -13,18 +13,19 @@
 //   * accumulators (128 lanes x Mt columns f32) live in TMEM; 8 TMEM A-slots of 64 k form the
 //     dequant -> MMA ring; tcgen05.commit releases A-slots / X stages and publishes the accumulator;
 //   * warp roles: 0 = weight-chunk producer, 2 = activation producer, 1 = TMEM allocator + single-thread
-//     MMA issuer, 4..11 = dequant + epilogue (tcgen05.ld -> bias -> global).
+//     MMA issuer, 4..11 = dequant (8 warps) + epilogue (tcgen05.ld -> bias -> global).
 #include "formats.cuh"
 #include "internal.h"
 
 namespace b200q {
 
-constexpr int GT_THREADS = 384;
-constexpr int GT_NX = 4;       // activation sub-stage ring (64 k each)
-constexpr int GT_ASLOTS = 8;   // TMEM A slots (32 columns = 64 k of f16 each)
+constexpr int GT_DQ_WARPS = 8;                     // dequant warps: 2 per TMEM lane quarter, each half of the chunk's k (16 warps measured slower)
+constexpr int GT_THREADS = (4 + GT_DQ_WARPS) * 32;
+constexpr int GT_NX = 16;      // max activation sub-stage ring depth (64 k each); runtime depth p.nx
+constexpr int GT_ASLOTS = 3;   // max TMEM A slots; one slot = one whole 256-k chunk of f16 (128 columns)
 constexpr int GT_MAX_NW = 4;   // weight chunk ring
 constexpr int GT_D_COL = 0;    // accumulator columns [0, 256)
-constexpr int GT_A_COL = 256;  // A slots in columns [256, 512)
+// A slots occupy the top of TMEM: columns [512 - 128*nslots, 512); 2 slots when Mt > 128, else 3
 constexpr int GT_HDR = 1024;
 
 struct GemmParams {
@@ -36,6 +37,9 @@ struct GemmParams {
     int y_dtype;
     int T, KC, MT, Mt;
     int gpc, chunk_bytes, nw, w_stage_bytes, x_stage_bytes;
+    int nslots, a_col, nx;
+    int splits;        // split-K factor (serial K loop is the latency floor when there are fewer tiles than SMs)
+    float* partial;    // [splits][M][N] f32 when splits > 1
     uint32_t idesc;
 };
 
@@ -82,24 +86,31 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ float small_int_to_float(int q) { return __int_as_float(0x4B400000 + q) - 12582912.0f; }
-
-// 32 weights of a unit -> 16 packed f16 pairs in k order:  w = a*(v-off) - b
+// 32 integer weights of a unit (one byte each) -> 16 packed f16 pairs  w = a*(v-off) - b,  rounded once to f16.
+// Bytes become f16 with the 0x6400 trick (0x6400 | v == 1024 + v exactly), the integer offset is removed with an
+// exact HSUB2 and the scale/min applied with one HFMA2: ~1.75 instructions per weight, no I2F, no PRMT.
+// Pair order: word k yields (e0,e2) then (e1,e3) -- the activation staging kernel applies the same [0,2,1,3]
+// permutation inside every group of 4 k, so the contraction is unchanged.
+template <bool SIGNED>
 __device__ __forceinline__ void unit_to_f16(const Unit& u, uint32_t* out) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int h = k >> 2;
-        const uint32_t wv = u.v[k];
-        float f[4];
+    for (int h = 0; h < 2; h++) {
+        const float offf = 1024.0f + (float)u.off[h] + (SIGNED ? 128.0f : 0.0f);
+        const __half2 off2 = __float2half2_rn(offf);         // integer <= 2047: exact in f16
+        const __half2 a2 = __float2half2_rn(u.a[h]);
+        const __half2 nb2 = __float2half2_rn(-u.b[h]);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            int q = (int)(int8_t)((wv >> (8 * c)) & 0xFFu) - u.off[h];
-            f[c] = fmaf(u.a[h], small_int_to_float(q), -u.b[h]);
+        for (int k = 4 * h; k < 4 * h + 4; k++) {
+            const uint32_t wv = SIGNED ? (u.v[k] ^ 0x80808080u) : u.v[k];
+            uint32_t p02 = (wv & 0x00FF00FFu) | 0x64006400u;          // (1024 + e0, 1024 + e2)
+            uint32_t p13 = ((wv >> 8) & 0x00FF00FFu) | 0x64006400u;   // (1024 + e1, 1024 + e3)
+            __half2 x02 = __hsub2(*reinterpret_cast<__half2*>(&p02), off2);
+            __half2 x13 = __hsub2(*reinterpret_cast<__half2*>(&p13), off2);
+            x02 = __hfma2(x02, a2, nb2);
+            x13 = __hfma2(x13, a2, nb2);
+            out[2 * k] = *reinterpret_cast<uint32_t*>(&x02);
+            out[2 * k + 1] = *reinterpret_cast<uint32_t*>(&x13);
         }
-        __half2 p0 = __floats2half2_rn(f[0], f[1]);
-        __half2 p1 = __floats2half2_rn(f[2], f[3]);
-        out[2 * k] = *reinterpret_cast<uint32_t*>(&p0);
-        out[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p1);
     }
 }
 
@@ -115,13 +126,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
     uint64_t* d_full = a_empty + GT_ASLOTS;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_full + 1);
     uint8_t* xst = smem + GT_HDR;
-    uint8_t* wst = xst + (size_t)GT_NX * p.x_stage_bytes;
+    uint8_t* wst = xst + (size_t)p.nx * p.x_stage_bytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < p.nw; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 8); }
-        for (int s = 0; s < GT_NX; s++) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
-        for (int s = 0; s < GT_ASLOTS; s++) { mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < p.nw; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], GT_DQ_WARPS); }
+        for (int s = 0; s < p.nx; s++) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+        for (int s = 0; s < p.nslots; s++) { mbar_init(&a_full[s], GT_DQ_WARPS); mbar_init(&a_empty[s], 1); }
         mbar_init(d_full, 1);
         fence_mbar_init();
         fence_proxy_async();
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
-    const int total_tiles = p.T * p.MT;
+    const int total_tiles = p.T * p.MT * p.splits;
     const int KS = p.KC * 4;  // 64-k sub-stages along K
 
     if (warp == 0) {
@@ -145,9 +156,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
             int s = 0;
             uint32_t ph = 1;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int t = tile / p.MT;
-                const uint8_t* src = p.w + (size_t)t * p.KC * p.chunk_bytes;
-                for (int kc = 0; kc < p.KC; kc++) {
+                const int sp_ = tile % p.splits, t = (tile / p.splits) / p.MT;
+                const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                const uint8_t* src = p.w + ((size_t)t * p.KC + kc0) * p.chunk_bytes;
+                for (int kc = kc0; kc < kc1; kc++) {
                     mbar_wait(&empty_w[s], ph);
                     mbar_arrive_expect_tx(&full_w[s], (uint32_t)p.chunk_bytes);
                     if (p.MT == 1) bulk_g2s_hint(wst + (size_t)s * p.w_stage_bytes, src, (uint32_t)p.chunk_bytes, &full_w[s], pol);
@@ -163,14 +175,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
             int s = 0;
             uint32_t ph = 1;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % p.MT;
-                const uint8_t* src = p.xs + (size_t)mt * KS * p.x_stage_bytes;
-                for (int ks = 0; ks < KS; ks++) {
+                const int sp_ = tile % p.splits, mt = (tile / p.splits) % p.MT;
+                const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                const uint8_t* src = p.xs + ((size_t)mt * KS + 4 * kc0) * p.x_stage_bytes;
+                for (int ks = 4 * kc0; ks < 4 * kc1; ks++) {
                     mbar_wait(&empty_x[s], ph);
                     mbar_arrive_expect_tx(&full_x[s], (uint32_t)p.x_stage_bytes);
                     bulk_g2s(xst + (size_t)s * p.x_stage_bytes, src, (uint32_t)p.x_stage_bytes, &full_x[s]);
                     src += p.x_stage_bytes;
-                    if (++s == GT_NX) { s = 0; ph ^= 1u; }
+                    if (++s == p.nx) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -180,51 +193,57 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
             int xs = 0, as = 0;
             uint32_t xph = 0, aph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                for (int ks = 0; ks < KS; ks++) {
-                    mbar_wait(&a_full[as], aph);
-                    mbar_wait(&full_x[xs], xph);
-                    tc_fence_after();
-                    const uint32_t a_addr = tmem + GT_A_COL + as * 32;
-                    const uint64_t bdesc = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
+                const int sp_ = tile % p.splits;
+                const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                for (int kc = kc0; kc < kc1; kc++) {
+                    mbar_wait(&a_full[as], aph);  // a whole dequantised chunk (4 x 64 k) is in TMEM
+                    const uint32_t a_chunk = tmem + p.a_col + as * 128;
+#pragma unroll 1
+                    for (int j = 0; j < 4; j++) {
+                        mbar_wait(&full_x[xs], xph);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++)
-                        tc_mma_ts(tmem + GT_D_COL, a_addr + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, (ks | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < 4; kk++)
+                            tc_mma_ts(tmem + GT_D_COL, a_chunk + j * 32 + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
+                        tc_commit(&empty_x[xs]);
+                        if (++xs == p.nx) { xs = 0; xph ^= 1u; }
+                    }
                     tc_commit(&a_empty[as]);
-                    tc_commit(&empty_x[xs]);
-                    if (++xs == GT_NX) { xs = 0; xph ^= 1u; }
-                    if (++as == GT_ASLOTS) { as = 0; aph ^= 1u; }
+                    if (++as == p.nslots) { as = 0; aph ^= 1u; }
                 }
                 tc_commit(d_full);
             }
         }
     } else if (warp >= 4) {
         // ===================== dequant (thread == weight row) + epilogue =====================
-        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int q = warp & 3, h = (warp - 4) >> 2;  // lane quarter; k half (units 2j+h) and epilogue column half
         const int r = 32 * q + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
         const FmtMeta meta{p.gpc};
         int ws = 0, as = 0;
         uint32_t wph = 0, aph = 1, dph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int t = tile / p.MT, mt = tile % p.MT;
-            for (int kc = 0; kc < p.KC; kc++) {
+            const int sp_ = tile % p.splits, t = (tile / p.splits) / p.MT, mt = (tile / p.splits) % p.MT;
+            const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+            for (int kc = kc0; kc < kc1; kc++) {
                 mbar_wait(&full_w[ws], wph);
                 const uint8_t* wc = wst + (size_t)ws * p.w_stage_bytes;
+                mbar_wait(&a_empty[as], aph);  // the MMAs that read this TMEM slot two/three chunks ago are done
+                tc_fence_after();
 #pragma unroll 1
                 for (int j = 0; j < 4; j++) {
                     Unit u;
                     F::template load_unit<true>(wc, r, 2 * j + h, u, meta);
                     uint32_t pk[16];
-                    unit_to_f16(u, pk);
-                    mbar_wait(&a_empty[as], aph);
-                    tc_fence_after();
-                    tc_st16(lane_base + GT_A_COL + as * 32 + 16 * h, pk);
-                    tc_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[as]);
-                    if (++as == GT_ASLOTS) { as = 0; aph ^= 1u; }
+                    unit_to_f16<F::SIGNED>(u, pk);
+                    tc_st16(lane_base + p.a_col + as * 128 + j * 32 + 16 * h, pk);
                 }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[as]);
+                if (++as == p.nslots) { as = 0; aph ^= 1u; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_w[ws]);
                 if (++ws == p.nw) { ws = 0; wph ^= 1u; }
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
             const int64_t n = (int64_t)t * TILE_ROWS + r;
             const float bv = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
             const int half_cols = p.Mt >> 1;
-            for (int cb = 0; cb < half_cols; cb += 16) {
+            for (int cb = 0; cb < (h < 2 ? half_cols : 0); cb += 16) {
                 uint32_t v[16];
                 tc_ld16(lane_base + GT_D_COL + h * half_cols + cb, v);
                 tc_wait_ld();
@@ -244,7 +263,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
 #pragma unroll
                     for (int c = 0; c < 16; c++) {
                         const int64_t m = (int64_t)mt * p.Mt + h * half_cols + cb + c;
-                        if (m < p.M) store_out(p.y, p.y_dtype, m * p.ldy + n, __uint_as_float(v[c]) + bv);
+                        if (m < p.M) {
+                            if (p.splits > 1) p.partial[((size_t)sp_ * p.M + m) * p.N + n] = __uint_as_float(v[c]);
+                            else store_out(p.y, p.y_dtype, m * p.ldy + n, __uint_as_float(v[c]) + bv);
+                        }
                     }
                 }
             }
@@ -270,12 +292,32 @@ __global__ void stage_x_kernel(const void* __restrict__ x, int x_dtype, int64_t 
     const int kk = threadIdx.x;                                          // 0..63
     const int64_t mt = m / Mt;
     const int mr = (int)(m % Mt);
-    const int64_t k = (int64_t)ks * 64 + kk;
+    // position kk of the sub-stage holds source element (kk & ~3) | {0,2,1,3}[kk & 3]  (see unit_to_f16)
+    const int64_t k = (int64_t)ks * 64 + ((kk & ~3) | (((kk & 1) << 1) | ((kk >> 1) & 1)));
     float v = 0.0f;
     if (m < M && k < K) v = load_in(x, x_dtype, m * ldx + (perm ? perm[k] : k));
     v = fminf(fmaxf(v, -65504.0f), 65504.0f);
     uint8_t* dst = xs + ((size_t)(mt * KS + ks) * Mt) * 128 + (size_t)mr * 128 + ((((kk >> 3) ^ (mr & 7)) << 4) + ((kk & 7) << 1));
     *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+}
+
+// split-K reduction: y[m,n] = sum_s partial[s][m][n] (+ bias), summed in split order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N, const float* __restrict__ bias, void* y,
+                                     int y_dtype, int64_t ldy) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const int64_t m = idx / N, n = idx % N;
+    float acc = 0.0f;
+    for (int s = 0; s < splits; s++) acc += partial[((size_t)s * M + m) * N + n];
+    store_out(y, y_dtype, m * ldy + n, acc + (bias ? bias[n] : 0.0f));
+}
+
+static int pick_splits(const b200q_weight* w, int MT) {
+    int64_t tiles = w->T * MT;
+    int s = (int)(w->num_sms / tiles);
+    if (s > 8) s = 8;
+    if (s > (int)w->KC) s = (int)w->KC;
+    return s < 1 ? 1 : s;
 }
 
 static int pick_mt(int64_t M, int* MT) {
@@ -290,7 +332,9 @@ size_t gemm_ws_bytes(const b200q_weight* w, int64_t M) {
     if (M < 1) return 0;
     int MT;
     int Mt = pick_mt(M, &MT);
-    return (size_t)MT * Mt * (size_t)w->K_pad * 2;
+    size_t xs = ((size_t)MT * Mt * (size_t)w->K_pad * 2 + 255) & ~(size_t)255;
+    int S = pick_splits(w, MT);
+    return xs + (S > 1 ? (size_t)S * M * w->N * sizeof(float) : 0);
 }
 
 template <class F>
@@ -341,22 +385,37 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     p.chunk_bytes = w->chunk_bytes;
     p.w_stage_bytes = (w->chunk_bytes + 127) & ~127;
     p.x_stage_bytes = Mt * 128;
-    int avail = 227 * 1024 - GT_HDR - GT_NX * p.x_stage_bytes;
+    // activation ring: deep enough to cover the L2 latency when the MMAs are short (small Mt), <= 128 KB
+    int nx = (128 * 1024) / p.x_stage_bytes;
+    if (nx > GT_NX) nx = GT_NX;
+    if (nx < 4) nx = 4;
+    p.nx = nx;
+    int avail = 227 * 1024 - GT_HDR - nx * p.x_stage_bytes;
     int nw = avail / p.w_stage_bytes;
     if (nw > GT_MAX_NW) nw = GT_MAX_NW;
     if (nw < 2) return cudaErrorNotSupported;
     p.nw = nw;
+    p.nslots = Mt > 128 ? 2 : 3;
+    p.a_col = 512 - 128 * p.nslots;
     p.idesc = (1u << 4) | ((uint32_t)(Mt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major A/B, M=128, N=Mt
-    int smem = GT_HDR + GT_NX * p.x_stage_bytes + nw * p.w_stage_bytes;
-    int64_t tiles = (int64_t)p.T * MT;
+    int smem = GT_HDR + nx * p.x_stage_bytes + nw * p.w_stage_bytes;
+    p.splits = pick_splits(w, MT);
+    p.partial = reinterpret_cast<float*>(ws + (((size_t)MT * Mt * (size_t)w->K_pad * 2 + 255) & ~(size_t)255));
+    int64_t tiles = (int64_t)p.T * MT * p.splits;
     int grid = (int)(tiles < w->num_sms ? tiles : w->num_sms);
+    cudaError_t ge;
     switch (w->family) {
-        case B200Q_FAM_Q4_K: return launch_gemm_t<FmtQ4K>(p, grid, smem, st);
-        case B200Q_FAM_Q6_K: return launch_gemm_t<FmtQ6K>(p, grid, smem, st);
-        case B200Q_FAM_Q8_0: return launch_gemm_t<FmtQ8_0>(p, grid, smem, st);
-        case B200Q_FAM_G4: return launch_gemm_t<FmtG4>(p, grid, smem, st);
+        case B200Q_FAM_Q4_K: ge = launch_gemm_t<FmtQ4K>(p, grid, smem, st); break;
+        case B200Q_FAM_Q6_K: ge = launch_gemm_t<FmtQ6K>(p, grid, smem, st); break;
+        case B200Q_FAM_Q8_0: ge = launch_gemm_t<FmtQ8_0>(p, grid, smem, st); break;
+        case B200Q_FAM_G4: ge = launch_gemm_t<FmtG4>(p, grid, smem, st); break;
         default: return cudaErrorNotSupported;
     }
+    if (ge != cudaSuccess || p.splits == 1) return ge;
+    const int64_t total = M * w->N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.splits, M, w->N, w->bias, y, y_dtype, ldy);
+    count_launch();
+    return cudaGetLastError();
 }
 
 }  // namespace b200q

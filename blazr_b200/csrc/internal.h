@@ -39,13 +39,23 @@ cudaError_t launch_to_bf16(const void* x, int x_dtype, int64_t M, int64_t K, int
 
 // ---- matvec.cu ----
 struct MatvecPlan {
-    int grid, nstages, stage_bytes, smem_bytes, mb;
+    int grid, nstages, stage_bytes, smem_bytes, mb, xhat_bytes;
 };
-cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan);
+struct FusedPrologue {
+    int mode;  // 1 = add + rmsnorm + quant, 2 = swiglu + quant
+    const float* h_in;
+    const float* delta;
+    float* h_out;
+    const float* norm_w;
+    float eps;
+    const float* gate_up;
+};
+cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int pro = 0);
 size_t matvec_ws_bytes(const b200q_weight* w, int64_t M);  // counters + partials (excludes the activation buffer)
 void set_matvec_trace(long long* dev_buf);
 cudaError_t launch_l2_prefetch(const b200q_weight* w, int64_t M, int64_t max_bytes, cudaStream_t st);
-cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st);
+cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
+                          const FusedPrologue* fp = nullptr);
 
 // ---- gemm_tc.cu ----
 size_t gemm_ws_bytes(const b200q_weight* w, int64_t M);

@@ -190,7 +190,7 @@ cudaError_t launch_dequantize(const b200q_weight* w, void* out, int dtype, cudaS
 }
 
 // ------------------------------------------------------------------------------------------------
-// activation quantiser: per 32-element block d = amax/127, q = roundf(x/d) (oracle orc_quantize_act).
+// activation quantiser: per 32-element block d = amax/127, id = 1/d, q = roundf(x*id) (oracle orc_quantize_act).
 // Output records, chunk-major so the matvec brings one k-chunk of all M rows with one bulk copy:
 //   xq[(kc*M + m)*320] = { int8 q[256]; float d[8]; (int16 bsum16[2])[8] }
 // One CTA of 256 threads per (kc, m); warp == 32-block.
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) act_quant_kernel(const void* __restrict__
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     float d = __fdiv_rn(amax, 127.0f);
-    int q = (amax == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v, d));
+    const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+    int q = (int)roundf(__fmul_rn(v, id));
     int s = q;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);  // sum within each 16-lane half

@@ -41,6 +41,16 @@ struct MatvecParams {
     long long* trace;  // debug: 4 x globaltimer per CTA (null in production)
     int debug_flags;   // debug: bit0 = consumers skip the math (measures the pure TMA stream)
     int l2_prefetch_chunks;  // per CTA: chunks beyond the smem ring to pull into L2 before griddepcontrol.wait
+    // fused activation producers (prologue): 0 = records arrive by TMA from xq, 1 = quant(rmsnorm(h_in + delta) * nw),
+    // 2 = quant(silu(gate) * up).  The whole quantised activation then lives in shared memory for the CTA's life.
+    int pro;
+    int xhat_bytes;
+    const float* h_in;
+    const float* delta;
+    float* h_out;
+    const float* norm_w;
+    float eps;
+    const float* gate_up;
 };
 
 __device__ __forceinline__ int64_t sk_begin(int64_t g, int64_t C, int64_t G) { return g * C / G; }
@@ -72,12 +82,123 @@ __device__ __forceinline__ SkPlan sk_plan(int64_t c0, int64_t c1, int64_t KC) {
     return s;
 }
 
-template <class F, int MB>
+// ------------------------------------------------------------------------------------------------
+// Fused activation producers.  Executed by the 16 consumer warps after griddepcontrol.wait, while the first
+// ring-full of weight chunks (requested before the wait) is still in flight, so the separate norm / SwiGLU
+// kernels of a decode step (and their launch + drain gaps) disappear.  Arithmetic is identical to
+// decode_ops.cu (f64 sum of squares, explicit f32 ops, deterministic exp) => same bits as the oracle.
+// Records: xhat[(kc*M + m)*320] = { int8 q[256]; float d[8]; (int16 bsum16[2])[8] }.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quant_block_to_record(float v, uint8_t* rec, int blk_in_chunk, int lane) {
+    float amax = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float d = __fdiv_rn(amax, 127.0f);
+    const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+    const int q = (int)roundf(__fmul_rn(v, id));
+    int s = q;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int s_hi = __shfl_sync(0xffffffffu, s, 16);
+    rec[blk_in_chunk * 32 + lane] = (uint8_t)(int8_t)q;
+    if (lane == 0) {
+        reinterpret_cast<float*>(rec + 256)[blk_in_chunk] = d;
+        reinterpret_cast<uint32_t*>(rec + 288)[blk_in_chunk] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
+    }
+}
+
+template <int MB>
+__device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* xhat, int tid, int warp, int lane, bool writer) {
+    constexpr int NT = MV_CONSUMER_WARPS * 32;
+    const int K = (int)p.KC * CHUNK_K;
+    const int nblk = K / 32;
+    if (p.pro == 1) {
+        // ---- h = h_in (+ delta); xhat = quant(rmsnorm(h) * w) ----
+        // warp w owns the 32-blocks w, w+16, ...; every element is loaded once (all loads in flight together),
+        // kept in registers for the sum of squares and then normalised + quantised from registers.
+        constexpr int VMAX = 16;  // K <= 8192
+        __shared__ double red[MB][MV_CONSUMER_WARPS];
+        __shared__ float s_inv[MB];
+        const int nv = (nblk + MV_CONSUMER_WARPS - 1) / MV_CONSUMER_WARPS;
+        float v[MB][VMAX];
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+            if (m >= p.M) break;
+            const float* hr = p.h_in + (size_t)m * K;
+            const float* dr = p.delta ? p.delta + (size_t)m * K : nullptr;
+#pragma unroll
+            for (int j = 0; j < VMAX; j++) {
+                const int b = warp + j * MV_CONSUMER_WARPS;
+                v[m][j] = (j < nv && b < nblk) ? hr[b * 32 + lane] : 0.0f;
+            }
+            if (dr) {
+#pragma unroll
+                for (int j = 0; j < VMAX; j++) {
+                    const int b = warp + j * MV_CONSUMER_WARPS;
+                    if (j < nv && b < nblk) v[m][j] = __fadd_rn(v[m][j], dr[b * 32 + lane]);
+                }
+            }
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < VMAX; j += 2) {
+                s0 = fma((double)v[m][j], (double)v[m][j], s0);
+                s1 = fma((double)v[m][j + 1], (double)v[m][j + 1], s1);
+            }
+            double ss = s0 + s1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) red[m][warp] = ss;
+            if (writer && p.h_out) {
+#pragma unroll
+                for (int j = 0; j < VMAX; j++) {
+                    const int b = warp + j * MV_CONSUMER_WARPS;
+                    if (j < nv && b < nblk) p.h_out[(size_t)m * K + b * 32 + lane] = v[m][j];
+                }
+            }
+        }
+        named_bar_sync(4, NT);
+        if (tid < p.M) {
+            double tot = 0.0;
+#pragma unroll
+            for (int i = 0; i < MV_CONSUMER_WARPS; i++) tot += red[tid][i];
+            s_inv[tid] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)K), p.eps)));
+        }
+        named_bar_sync(4, NT);
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+            if (m >= p.M) break;
+            const float inv = s_inv[m];
+#pragma unroll
+            for (int j = 0; j < VMAX; j++) {
+                const int b = warp + j * MV_CONSUMER_WARPS;
+                if (j < nv && b < nblk) {
+                    const float x = __fmul_rn(__fmul_rn(v[m][j], inv), p.norm_w[b * 32 + lane]);
+                    quant_block_to_record(x, xhat + ((size_t)(b >> 3) * p.M + m) * ACT_REC_BYTES, b & 7, lane);
+                }
+            }
+        }
+    } else {
+        // ---- xhat = quant(silu(gate) * up), gate_up[M, 2K] ----
+        for (int m = 0; m < p.M; m++) {
+            const float* gr = p.gate_up + (size_t)m * 2 * K;
+            for (int b = warp; b < nblk; b += MV_CONSUMER_WARPS) {
+                const int k = b * 32 + lane;
+                const float gv = gr[k], uv = gr[K + k];
+                const float v = __fmul_rn(__fdiv_rn(gv, __fadd_rn(1.0f, det_expf(-gv))), uv);
+                quant_block_to_record(v, xhat + ((size_t)(b >> 3) * p.M + m) * ACT_REC_BYTES, b & 7, lane);
+            }
+        }
+    }
+    named_bar_sync(4, NT);  // records visible to every consumer warp
+}
+
+template <class F, int MB, bool PRO>
 __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + MV_MAX_STAGES;
-    uint8_t* stages = smem + MV_HDR_BYTES;
+    uint8_t* xhat = smem + MV_HDR_BYTES;                  // fused prologue: quantised activation records [kc][m][320]
+    uint8_t* stages = smem + MV_HDR_BYTES + (PRO ? p.xhat_bytes : 0);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t G = gridDim.x, g = blockIdx.x;
@@ -109,7 +230,7 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
         // ===================== producer: one thread drives the TMA engine =====================
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
-            const uint32_t xbytes = (uint32_t)p.M * ACT_REC_BYTES;
+            const uint32_t xbytes = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
             const uint32_t wbytes = (uint32_t)p.chunk_bytes;
             // j-th processed chunk -> (weight address, k-chunk index)
             const uint8_t* base = p.w + c0 * (int64_t)wbytes;
@@ -137,8 +258,9 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(chunk_src(j)), "r"(wbytes) : "memory");
             pdl_wait();  // activations (written by the preceding kernel) are visible from here on
             if (p.trace) p.trace[g * 8 + 4] = globaltimer_ns();
-            for (int j = 0; j < pre; j++)
-                bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[j]);
+            if (!PRO)
+                for (int j = 0; j < pre; j++)
+                    bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[j]);
             int s = 0;
             uint32_t ph = 0;  // second use of each stage waits for the consumers' first release (phase 0)
             for (int j = pre; j < n_chunks; j++) {
@@ -146,7 +268,7 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
                 uint8_t* st = stages + (size_t)s * p.stage_bytes;
                 mbar_arrive_expect_tx(&full[s], wbytes + xbytes);
                 bulk_g2s_hint(st, chunk_src(j), wbytes, &full[s], pol);
-                bulk_g2s(st + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[s]);
+                if (!PRO) bulk_g2s(st + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[s]);
                 if (++s == nst) { s = 0; ph ^= 1u; }
             }
         }
@@ -220,7 +342,10 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
 #pragma unroll
         for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
 
+    if (PRO) fused_prologue<MB>(p, xhat, tid, warp, lane, g == 0);
+
     // segment walk: 0 = head (partial, slot 0), 1 = tail (partial, slot 1), 2 = full tiles
+    int kcur = sp.nH > 0 ? sp.kcH : 0;  // k-chunk index of the chunk being processed (fused prologue addressing)
     int seg = sp.nH > 0 ? 0 : (sp.nT > 0 ? 1 : 2);
     int seg_left = seg == 0 ? sp.nH : (seg == 1 ? sp.nT : KC);  // chunks until the next flush
     int t = seg == 0 ? sp.tH : (seg == 1 ? sp.tT : sp.tF);
@@ -230,7 +355,8 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
         mbar_wait(&full[s], ph);
         if (p.trace && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
         const uint8_t* wc = stages + (size_t)s * p.stage_bytes;
-        const uint8_t* xr = wc + p.chunk_bytes;
+        const uint8_t* xr = PRO ? xhat + (size_t)kcur * p.M * ACT_REC_BYTES : wc + p.chunk_bytes;
+        if (PRO) { if (++kcur == KC) kcur = 0; }
 
         uint4 xa[MB], xb[MB];
         float dx[MB];
@@ -324,8 +450,8 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
             for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
 
         // ---- next segment / tile ----
-        if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; }
-        else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; }
+        if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; kcur = 0; }
+        else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; kcur = 0; }
         else { seg_left = KC; t++; }
 
     }
@@ -358,13 +484,13 @@ __global__ void __launch_bounds__(32) l2_prefetch_kernel(const uint8_t* __restri
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <class F, int MB>
+template <class F, int MB, bool PRO>
 static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStream_t st) {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -378,7 +504,7 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB>, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO>, p);
     if (le != cudaSuccess) return le;
     count_launch();
     return cudaGetLastError();
@@ -387,9 +513,9 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
 template <class F>
 static cudaError_t launch_f(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
     switch (mb) {
-        case 1: return launch_t<F, 1>(p, grid, smem, st);
-        case 2: return launch_t<F, 2>(p, grid, smem, st);
-        case 4: return launch_t<F, 4>(p, grid, smem, st);
+        case 1: return p.pro ? launch_t<F, 1, true>(p, grid, smem, st) : launch_t<F, 1, false>(p, grid, smem, st);
+        case 2: return p.pro ? launch_t<F, 2, true>(p, grid, smem, st) : launch_t<F, 2, false>(p, grid, smem, st);
+        case 4: return p.pro ? launch_t<F, 4, true>(p, grid, smem, st) : launch_t<F, 4, false>(p, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -398,17 +524,18 @@ static long long* g_trace = nullptr;
 static int g_trace_launch = 0;
 void set_matvec_trace(long long* p) { g_trace = p; g_trace_launch = 0; }
 
-cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan) {
+cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int pro) {
     if (M < 1 || M > 4) return cudaErrorInvalidValue;
     int mb = M == 1 ? 1 : (M == 2 ? 2 : 4);
-    int stage = w->chunk_bytes + (int)M * ACT_REC_BYTES;
+    int stage = w->chunk_bytes + (pro ? 0 : (int)M * ACT_REC_BYTES);
     stage = (stage + 127) & ~127;
+    int xhat = pro ? (int)(((size_t)w->KC * M * ACT_REC_BYTES + 127) & ~(size_t)127) : 0;
     // > half an SM on purpose: two CTAs of one launch must never share an SM (measured: after glue kernels perturb
     // the placement, doubled-up CTAs run at half speed and the launch takes 2x); cross-launch overlap is done
     // with the L2 prefetch kernel instead
     int budget_kb = 150;
     if (const char* e = getenv("B200Q_MV_SMEM_KB")) { int v = atoi(e); if (v >= 64 && v <= 224) budget_kb = v; }
-    int budget = budget_kb * 1024 - MV_HDR_BYTES;
+    int budget = budget_kb * 1024 - MV_HDR_BYTES - xhat;
     int nst = budget / stage;
     if (nst > MV_MAX_STAGES) nst = MV_MAX_STAGES;
     if (const char* e = getenv("B200Q_MV_STAGES")) { int v = atoi(e); if (v >= 2 && v < nst) nst = v; }
@@ -420,7 +547,8 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan) {
     plan->grid = (int)G;
     plan->nstages = nst;
     plan->stage_bytes = stage;
-    plan->smem_bytes = MV_HDR_BYTES + nst * stage;
+    plan->smem_bytes = MV_HDR_BYTES + xhat + nst * stage;
+    plan->xhat_bytes = xhat;
     plan->mb = mb;
     return cudaSuccess;
 }
@@ -433,9 +561,11 @@ size_t matvec_ws_bytes(const b200q_weight* w, int64_t M) {
     return cnt + part;
 }
 
-cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st) {
+cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
+                          const FusedPrologue* fp) {
     MatvecPlan plan;
-    cudaError_t e = matvec_plan(w, M, &plan);
+    const int pro = fp ? fp->mode : 0;
+    cudaError_t e = matvec_plan(w, M, &plan, pro);
     if (e != cudaSuccess) return e;
     MatvecParams p;
     p.w = w->data;
@@ -455,6 +585,14 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.nstages = plan.nstages;
     p.chunk_bytes = w->chunk_bytes;
     p.stage_bytes = plan.stage_bytes;
+    p.pro = pro;
+    p.xhat_bytes = plan.xhat_bytes;
+    p.h_in = fp ? fp->h_in : nullptr;
+    p.delta = fp ? fp->delta : nullptr;
+    p.h_out = fp ? fp->h_out : nullptr;
+    p.norm_w = fp ? fp->norm_w : nullptr;
+    p.eps = fp ? fp->eps : 0.0f;
+    p.gate_up = fp ? fp->gate_up : nullptr;
     p.trace = g_trace ? g_trace + (size_t)(g_trace_launch++) * 148 * 8 : nullptr;
     p.debug_flags = 0;
     {
@@ -479,7 +617,7 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
 namespace b200q {
 cudaError_t launch_l2_prefetch(const b200q_weight* w, int64_t M, int64_t max_bytes, cudaStream_t st) {
     MatvecPlan plan;
-    cudaError_t e = matvec_plan(w, M < 1 ? 1 : (M > 4 ? 4 : M), &plan);
+    cudaError_t e = matvec_plan(w, M < 1 ? 1 : (M > 4 ? 4 : M), &plan, 0);
     if (e != cudaSuccess) return e;
     int nchunks = (int)(max_bytes / ((int64_t)plan.grid * w->chunk_bytes));
     if (nchunks < 1) return cudaSuccess;

@@ -217,6 +217,7 @@ class Decoder:
         self.h = torch.zeros((M, H), **f32)
         self.h2 = torch.zeros((M, H), **f32)  # residual stream ping-pong (the fused add+norm is not in-place)
         self.delta = torch.zeros((M, H), **f32)
+        self.delta2 = torch.zeros((M, H), **f32)  # down_proj output (the fused o->norm reads delta while down writes)
         self.qkv = torch.zeros((M, self.qd + 2 * self.kvd), **f32)
         self.gu = torch.zeros((M, 2 * self.ff), **f32)
         self.logits_local = torch.zeros((M, v1 - v0), **f32)
@@ -226,6 +227,8 @@ class Decoder:
         act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
         self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
         import os as _os
+        self.fused = _os.environ.get("B200Q_FUSED", "0") != "0"   # add+norm+quant fused into the matvec prologue
+        self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0"  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
 
@@ -326,26 +329,51 @@ class Decoder:
                                                  C.c_int64(cfg.hidden), C.c_int64(M), P(self.xq_h), None, st))
             hin, hout = hout, hin
 
+        def matvec_norm(lins, w, out):
+            """norm fused into the matvec prologue (one launch per fused weight group; the first writes h_out)"""
+            nonlocal hin, hout
+            for j, ln in enumerate(lins):
+                ops._check(L.b200q_matmul_norm(ln.w.handle, P(hin), P(delta) if delta is not None else None, P(hout) if j == 0 else None, P(w),
+                                               C.c_float(cfg.eps), C.c_int64(M), C.c_void_p(out.data_ptr() + 4 * ln.col0), C.c_int32(ops.F32),
+                                               C.c_int64(out.stride(0)), C.c_void_p(ln.ws.data_ptr()), C.c_size_t(ln.ws.numel()), st))
+            hin, hout = hout, hin
+
+        fused = self.fused
         for li, lay in enumerate(self.layers):
-            norm(lay["attn_norm"])
-            self._matvec(lay["qkv"], self.xq_h, self.qkv)
-            self._prefetch(lay["o"])
+            if fused:
+                matvec_norm(lay["qkv"], lay["attn_norm"], self.qkv)
+            else:
+                norm(lay["attn_norm"])
+                self._matvec(lay["qkv"], self.xq_h, self.qkv)
             ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
                                            C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
                                            P(self.xq_attn), None, st))
             self._matvec(lay["o"], self.xq_attn, self.delta)
-            self._prefetch(lay["gu"])
             self._allreduce(self.delta)
             delta = self.delta
-            norm(lay["mlp_norm"])
-            self._matvec(lay["gu"], self.xq_h, self.gu)
-            self._prefetch(lay["down"])
-            ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
-            self._matvec(lay["down"], self.xq_ff, self.delta)
-            self._prefetch(self.layers[li + 1]["qkv"] if li + 1 < len(self.layers) else self.head)
-            self._allreduce(self.delta)
-        norm(self.final_norm)
-        self._matvec(self.head, self.xq_h, self.logits_local)
+            if fused:
+                matvec_norm(lay["gu"], lay["mlp_norm"], self.gu)
+            else:
+                norm(lay["mlp_norm"])
+                self._matvec(lay["gu"], self.xq_h, self.gu)
+            if self.fused_swiglu:
+                for ln in lay["down"]:
+                    ops._check(L.b200q_matmul_swiglu(ln.w.handle, P(self.gu), C.c_int64(M), C.c_void_p(self.delta2.data_ptr() + 4 * ln.col0),
+                                                     C.c_int32(ops.F32), C.c_int64(self.delta2.stride(0)), C.c_void_p(ln.ws.data_ptr()),
+                                                     C.c_size_t(ln.ws.numel()), st))
+                self._allreduce(self.delta2)
+                delta = self.delta2
+            else:
+                ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
+                self._matvec(lay["down"], self.xq_ff, self.delta2)
+                self._allreduce(self.delta2)
+                delta = self.delta2
+        if fused:
+            matvec_norm(self.head, self.final_norm, self.logits_local)
+        else:
+            norm(self.final_norm)
+        if not fused:
+            self._matvec(self.head, self.xq_h, self.logits_local)
         if self.world > 1:
             torch.distributed.all_gather_into_tensor(self.logits, self.logits_local, group=self.group)
             full = self.logits.permute(1, 0, 2).reshape(M, -1).contiguous()  # ranks hold consecutive vocab slices
@@ -355,9 +383,11 @@ class Decoder:
             ops._check(L.b200q_argmax(P(self.logits), C.c_int64(self.logits.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
 
     def launches_per_step(self) -> int:
-        n = 1 + 1 + len(self.head) + 1  # embed, final norm, head, argmax
+        glue = 0 if self.fused else 1
+        sw = 0 if self.fused_swiglu else 1
+        n = 1 + glue + len(self.head) + 1  # embed, (final norm), head, argmax
         for lay in self.layers:
-            n += 2 + len(lay["qkv"]) + 1 + len(lay["o"]) + len(lay["gu"]) + 1 + len(lay["down"])
+            n += 2 * glue + len(lay["qkv"]) + 1 + len(lay["o"]) + len(lay["gu"]) + sw + len(lay["down"])
         return n
 
     def capture(self):

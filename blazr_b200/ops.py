@@ -54,7 +54,7 @@ EXPORTS = [
     "b200q_weight_set_bias", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
-    "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2",
+    "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
 ]
 
 _lib = None

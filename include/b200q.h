@@ -139,6 +139,15 @@ int32_t b200q_quantize_act(const void* x, int32_t x_dtype, int64_t M, int64_t K,
                            void* xq, void* stream);
 int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* y, int32_t y_dtype, int64_t ldy,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Decode matmuls with a fused activation producer (M <= 4): the consumer warps build the quantised activation in
+ * shared memory while the first weight chunks are in flight, so no separate norm / SwiGLU kernel runs.
+ *   norm  : h = h_in (+ delta, nullable); h_out (nullable; written once) = h; x = quant(rmsnorm(h) * norm_w); y = x . W^T
+ *   swiglu: x = quant(silu(gate) * up) for gate_up[M, 2K] (gate first);           y = x . W^T
+ * Same arithmetic (bit for bit) as b200q_add_rmsnorm_quant / b200q_swiglu_quant followed by b200q_matmul_q8. */
+int32_t b200q_matmul_norm(const b200q_weight* w, const float* h_in, const float* delta, float* h_out, const float* norm_w, float eps, int64_t M,
+                          void* y, int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+int32_t b200q_matmul_swiglu(const b200q_weight* w, const float* gate_up, int64_t M, void* y, int32_t y_dtype, int64_t ldy, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* Hint: ask the TMA engine to pull the first `max_bytes` of w (in the order the next b200q_matmul_q8(w, M) will
  * stream them) into L2.  Enqueue it right after the preceding matmul: it overlaps the operators in between. */
 int32_t b200q_weight_prefetch_l2(const b200q_weight* w, int64_t M, int64_t max_bytes, void* stream);

@@ -260,7 +260,8 @@ void orc_dequant_ggml(int t, const uint8_t* blocks, int64_t nelem, float* out) {
 /*
  * Activation quantizer, per 32-element block ("Q8_1 style", the convention of dp4a matvec
  * kernels; boostr's CUDA side is described as dp4a kernels at reference README.md:120):
- *   d = amax / 127;  q = amax == 0 ? 0 : roundf(x / d)   (IEEE f32 divide, round half away)
+ *   d = amax / 127;  id = d ? 1/d : 0;  q = roundf(x * id)   (IEEE f32 ops, round half away) -- the ggml
+ *   quantize_row_q8_0 recipe, bit-exact with gguf.quants' Q8_0 quantizer (tests/golden)
  * bsum16[j] = sum of q over 16-element half blocks (int32).
  */
 void orc_quantize_act(const float* x, int64_t M, int64_t K, int8_t* q, float* d, int32_t* bsum16) {
@@ -271,10 +272,11 @@ void orc_quantize_act(const float* x, int64_t M, int64_t K, int8_t* q, float* d,
         float amax = 0.0f;
         for (int j = 0; j < 32; j++) { float v = fabsf(xb[j]); if (v > amax) amax = v; }
         float dd = amax / 127.0f;
+        float id = (dd != 0.0f) ? 1.0f / dd : 0.0f;
         d[i] = dd;
         int32_t s0 = 0, s1 = 0;
         for (int j = 0; j < 32; j++) {
-            int8_t v = (amax == 0.0f) ? 0 : (int8_t)roundf(xb[j] / dd);
+            int8_t v = (int8_t)roundf(xb[j] * id);
             q[i * 32 + j] = v;
             if (j < 16) s0 += v; else s1 += v;
         }

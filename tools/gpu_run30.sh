@@ -1,0 +1,3 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -q --maxfail=5 -p no:cacheprovider 2>&1 | tail -3
+timeout 600 python tools/kbench.py --fmts Q4_K,Q6_K --ms 32,2048 --quick 2>&1 | tail -16
