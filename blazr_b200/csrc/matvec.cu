@@ -1,462 +1,10 @@
-// matvec.cu -- decode-time dequant-matvec (M = 1..4): the HBM-bound hot kernel.
-//
-// Design (DESIGN.md "Kernel 1"):
-//   * stream-K over the tile-major chunk array: CTA g owns the contiguous chunk range
-//     [g*C/G, (g+1)*C/G)  -> every SM streams one contiguous region of HBM, perfect balance for any N,K;
-//   * one producer thread feeds a ring of shared-memory stages with cp.async.bulk (TMA engine, 1-D,
-//     mbarrier complete_tx): 1 copy of the 18-35 KB weight chunk + 1 copy of the M x 320 B quantised
-//     activation record per stage, so ~100 KB per SM are in flight independent of occupancy;
-//   * 16 consumer warps: warp w owns rows 8w..8w+7 of the tile, 8 lanes x 16 B walk one row's
-//     256-k chunk (unit i = 32 consecutive k), 4 rows per step; activations stay in registers for the
-//     8 rows; integer dot products with dp4a, per-sub-block scales applied in f32;
-//   * at tile end an 8-lane shuffle reduction; tiles split between CTAs are combined DETERMINISTICALLY
-//     through per-CTA partial slots in the workspace: the last CTA to arrive (atomic counter) sums the
-//     partials in CTA order and writes y (no float atomics, no inter-CTA waiting).
+// matvec.cu -- host side of the decode matvec: launch plan, workspace sizing, per-format dispatch, L2 prefetch hint.
+// The kernel lives in matvec_impl.cuh and is instantiated per format in inst_<format>.cu.
 #include <cstdlib>
 
-#include "formats.cuh"
-#include "internal.h"
+#include "matvec_common.cuh"
 
 namespace b200q {
-
-constexpr int MV_CONSUMER_WARPS = 16;
-constexpr int MV_THREADS = (MV_CONSUMER_WARPS + 2) * 32;  // + producer warp + fix-up warp
-constexpr int MV_ROWS_PER_WARP = TILE_ROWS / MV_CONSUMER_WARPS;  // 8
-constexpr int MV_STEPS = MV_ROWS_PER_WARP / 4;                    // 2 (4 rows per step, 8 lanes per row)
-constexpr int MV_MAX_STAGES = 10;
-constexpr int MV_HDR_BYTES = 256;  // barriers + flags
-
-struct MatvecParams {
-    const uint8_t* w;
-    const uint8_t* xq;
-    void* y;
-    const float* bias;
-    double* ws_part;
-    unsigned int* ws_cnt;
-    int64_t N;
-    int M, y_dtype;
-    int64_t ldy;
-    int64_t KC, C;
-    int gpc, nstages, chunk_bytes, stage_bytes;
-    long long* trace;  // debug: 4 x globaltimer per CTA (null in production)
-    int debug_flags;   // debug: bit0 = consumers skip the math (measures the pure TMA stream)
-    int l2_prefetch_chunks;  // per CTA: chunks beyond the smem ring to pull into L2 before griddepcontrol.wait
-    // fused activation producers (prologue): 0 = records arrive by TMA from xq, 1 = quant(rmsnorm(h_in + delta) * nw),
-    // 2 = quant(silu(gate) * up).  The whole quantised activation then lives in shared memory for the CTA's life.
-    int pro;
-    int xhat_bytes;
-    const float* h_in;
-    const float* delta;
-    float* h_out;
-    const float* norm_w;
-    float eps;
-    const float* gate_up;
-};
-
-__device__ __forceinline__ int64_t sk_begin(int64_t g, int64_t C, int64_t G) { return g * C / G; }
-__device__ __forceinline__ int64_t sk_owner(int64_t c, int64_t C, int64_t G) { return ((c + 1) * G - 1) / C; }
-
-// Processing order of a CTA's chunk range [c0,c1): the two tiles it shares with its neighbours first
-// (head = tail end of tile t_first, then tail = first chunks of tile t_last), the tiles it owns entirely last.
-// Both contributors of a split tile therefore finish their share early in their lifetime and the
-// fix-up (atomic arrival + ordered reduction by the last arriver) happens mid-stream instead of in the tail.
-struct SkPlan {
-    int nH, nT, nF;          // chunks in the head / tail / full segments
-    int kcH;                 // k-chunk index at which the head segment starts (tail and full start at 0)
-    int tH, tT, tF;          // tile indices: head tile, tail tile, first full tile
-};
-__device__ __forceinline__ SkPlan sk_plan(int64_t c0, int64_t c1, int64_t KC) {
-    SkPlan s;
-    const int64_t t0 = c0 / KC, t1 = (c1 - 1) / KC;
-    const int kc0 = (int)(c0 - t0 * KC);
-    const int64_t head_end = (kc0 != 0 || c1 < (t0 + 1) * KC) ? ((t0 + 1) * KC < c1 ? (t0 + 1) * KC : c1) : c0;
-    s.nH = (int)(head_end - c0);
-    s.kcH = kc0;
-    s.tH = (int)t0;
-    int64_t tail_begin = c1;
-    if (c1 > head_end && c1 != (t1 + 1) * KC) tail_begin = t1 * KC > head_end ? t1 * KC : head_end;
-    s.nT = (int)(c1 - tail_begin);
-    s.tT = (int)t1;
-    s.nF = (int)(tail_begin - head_end);
-    s.tF = (int)(head_end / KC);
-    return s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused activation producers.  Executed by the 16 consumer warps after griddepcontrol.wait, while the first
-// ring-full of weight chunks (requested before the wait) is still in flight, so the separate norm / SwiGLU
-// kernels of a decode step (and their launch + drain gaps) disappear.  Arithmetic is identical to
-// decode_ops.cu (f64 sum of squares, explicit f32 ops, deterministic exp) => same bits as the oracle.
-// Records: xhat[(kc*M + m)*320] = { int8 q[256]; float d[8]; (int16 bsum16[2])[8] }.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void quant_block_to_record(float v, uint8_t* rec, int blk_in_chunk, int lane) {
-    float amax = fabsf(v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    const float d = __fdiv_rn(amax, 127.0f);
-    const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
-    const int q = (int)roundf(__fmul_rn(v, id));
-    int s = q;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const int s_hi = __shfl_sync(0xffffffffu, s, 16);
-    rec[blk_in_chunk * 32 + lane] = (uint8_t)(int8_t)q;
-    if (lane == 0) {
-        reinterpret_cast<float*>(rec + 256)[blk_in_chunk] = d;
-        reinterpret_cast<uint32_t*>(rec + 288)[blk_in_chunk] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
-    }
-}
-
-template <int MB>
-__device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* xhat, int tid, int warp, int lane, bool writer) {
-    constexpr int NT = MV_CONSUMER_WARPS * 32;
-    const int K = (int)p.KC * CHUNK_K;
-    const int nblk = K / 32;
-    if (p.pro == 1) {
-        // ---- h = h_in (+ delta); xhat = quant(rmsnorm(h) * w) ----
-        // warp w owns the 32-blocks w, w+16, ...; every element is loaded once (all loads in flight together),
-        // kept in registers for the sum of squares and then normalised + quantised from registers.
-        constexpr int VMAX = 16;  // K <= 8192
-        __shared__ double red[MB][MV_CONSUMER_WARPS];
-        __shared__ float s_inv[MB];
-        const int nv = (nblk + MV_CONSUMER_WARPS - 1) / MV_CONSUMER_WARPS;
-        float v[MB][VMAX];
-#pragma unroll
-        for (int m = 0; m < MB; m++) {
-            if (m >= p.M) break;
-            const float* hr = p.h_in + (size_t)m * K;
-            const float* dr = p.delta ? p.delta + (size_t)m * K : nullptr;
-#pragma unroll
-            for (int j = 0; j < VMAX; j++) {
-                const int b = warp + j * MV_CONSUMER_WARPS;
-                v[m][j] = (j < nv && b < nblk) ? hr[b * 32 + lane] : 0.0f;
-            }
-            if (dr) {
-#pragma unroll
-                for (int j = 0; j < VMAX; j++) {
-                    const int b = warp + j * MV_CONSUMER_WARPS;
-                    if (j < nv && b < nblk) v[m][j] = __fadd_rn(v[m][j], dr[b * 32 + lane]);
-                }
-            }
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < VMAX; j += 2) {
-                s0 = fma((double)v[m][j], (double)v[m][j], s0);
-                s1 = fma((double)v[m][j + 1], (double)v[m][j + 1], s1);
-            }
-            double ss = s0 + s1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if (lane == 0) red[m][warp] = ss;
-            if (writer && p.h_out) {
-#pragma unroll
-                for (int j = 0; j < VMAX; j++) {
-                    const int b = warp + j * MV_CONSUMER_WARPS;
-                    if (j < nv && b < nblk) p.h_out[(size_t)m * K + b * 32 + lane] = v[m][j];
-                }
-            }
-        }
-        named_bar_sync(4, NT);
-        if (tid < p.M) {
-            double tot = 0.0;
-#pragma unroll
-            for (int i = 0; i < MV_CONSUMER_WARPS; i++) tot += red[tid][i];
-            s_inv[tid] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)K), p.eps)));
-        }
-        named_bar_sync(4, NT);
-#pragma unroll
-        for (int m = 0; m < MB; m++) {
-            if (m >= p.M) break;
-            const float inv = s_inv[m];
-#pragma unroll
-            for (int j = 0; j < VMAX; j++) {
-                const int b = warp + j * MV_CONSUMER_WARPS;
-                if (j < nv && b < nblk) {
-                    const float x = __fmul_rn(__fmul_rn(v[m][j], inv), p.norm_w[b * 32 + lane]);
-                    quant_block_to_record(x, xhat + ((size_t)(b >> 3) * p.M + m) * ACT_REC_BYTES, b & 7, lane);
-                }
-            }
-        }
-    } else {
-        // ---- xhat = quant(silu(gate) * up), gate_up[M, 2K] ----
-        for (int m = 0; m < p.M; m++) {
-            const float* gr = p.gate_up + (size_t)m * 2 * K;
-            for (int b = warp; b < nblk; b += MV_CONSUMER_WARPS) {
-                const int k = b * 32 + lane;
-                const float gv = gr[k], uv = gr[K + k];
-                const float v = __fmul_rn(__fdiv_rn(gv, __fadd_rn(1.0f, det_expf(-gv))), uv);
-                quant_block_to_record(v, xhat + ((size_t)(b >> 3) * p.M + m) * ACT_REC_BYTES, b & 7, lane);
-            }
-        }
-    }
-    named_bar_sync(4, NT);  // records visible to every consumer warp
-}
-
-template <class F, int MB, bool PRO>
-__global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + MV_MAX_STAGES;
-    uint8_t* xhat = smem + MV_HDR_BYTES;                  // fused prologue: quantised activation records [kc][m][320]
-    uint8_t* stages = smem + MV_HDR_BYTES + (PRO ? p.xhat_bytes : 0);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t G = gridDim.x, g = blockIdx.x;
-    if (p.trace && tid == 0) {
-        p.trace[g * 8 + 0] = globaltimer_ns();
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        p.trace[g * 8 + 2] = smid;
-    }
-    const int64_t c0 = sk_begin(g, p.C, G), c1 = sk_begin(g + 1, p.C, G);
-    const int n_chunks = (int)(c1 - c0);
-    const int KC = (int)p.KC;
-    const int nst = p.nstages;
-    SkPlan& sp = *reinterpret_cast<SkPlan*>(smem + 2 * MV_MAX_STAGES * 8);       // shared plan (computed once)
-
-    if (tid == 0) {
-        sp = sk_plan(c0, c1, p.KC);
-        for (int s = 0; s < nst; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], MV_CONSUMER_WARPS);
-        }
-        fence_mbar_init();
-        fence_proxy_async();
-    }
-    pdl_launch_dependents();  // let the next kernel of the stream start its own weight prefetch
-    __syncthreads();
-
-    if (warp == MV_CONSUMER_WARPS) {
-        // ===================== producer: one thread drives the TMA engine =====================
-        if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
-            const uint32_t xbytes = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
-            const uint32_t wbytes = (uint32_t)p.chunk_bytes;
-            // j-th processed chunk -> (weight address, k-chunk index)
-            const uint8_t* base = p.w + c0 * (int64_t)wbytes;
-            auto chunk_src = [&](int j) -> const uint8_t* {
-                if (j < sp.nH) return base + (size_t)j * wbytes;
-                if (j < sp.nH + sp.nT) return base + (size_t)(sp.nH + sp.nF + (j - sp.nH)) * wbytes;
-                return base + (size_t)(sp.nH + (j - sp.nH - sp.nT)) * wbytes;
-            };
-            auto chunk_kc = [&](int j) -> int {
-                if (j < sp.nH) return sp.kcH + j;
-                if (j < sp.nH + sp.nT) return j - sp.nH;
-                return (j - sp.nH - sp.nT) % KC;
-            };
-            // Phase 1 (before griddepcontrol.wait): weights do not depend on the preceding kernels.  Fill the
-            // shared-memory ring and ask the TMA engine to pull the rest of this CTA's range into L2, so HBM
-            // keeps streaming across the kernel boundary while the predecessor drains.
-            const int pre = n_chunks < nst ? n_chunks : nst;
-            for (int j = 0; j < pre; j++) {
-                mbar_arrive_expect_tx(&full[j], wbytes + xbytes);
-                bulk_g2s_hint(stages + (size_t)j * p.stage_bytes, chunk_src(j), wbytes, &full[j], pol);
-            }
-            int npf = n_chunks - pre;
-            if (npf > p.l2_prefetch_chunks) npf = p.l2_prefetch_chunks;
-            for (int j = pre; j < pre + npf; j++)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(chunk_src(j)), "r"(wbytes) : "memory");
-            pdl_wait();  // activations (written by the preceding kernel) are visible from here on
-            if (p.trace) p.trace[g * 8 + 4] = globaltimer_ns();
-            if (!PRO)
-                for (int j = 0; j < pre; j++)
-                    bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[j]);
-            int s = 0;
-            uint32_t ph = 0;  // second use of each stage waits for the consumers' first release (phase 0)
-            for (int j = pre; j < n_chunks; j++) {
-                mbar_wait(&empty[s], ph);
-                uint8_t* st = stages + (size_t)s * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[s], wbytes + xbytes);
-                bulk_g2s_hint(st, chunk_src(j), wbytes, &full[s], pol);
-                if (!PRO) bulk_g2s(st + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[s]);
-                if (++s == nst) { s = 0; ph ^= 1u; }
-            }
-        }
-        return;
-    }
-    if (warp == MV_CONSUMER_WARPS + 1) {
-        // ===================== fix-up warp: arrival atomics + ordered reduction of split tiles =====================
-        // Runs beside the consumers (they only bar.arrive), so neither the math nor the TMA stream ever waits
-        // for an atomic round trip.  Split tiles are processed first, so this finishes long before the CTA does.
-        if (sp.nH == 0 && sp.nT == 0) return;
-        pdl_wait();
-        // arrival bookkeeping is computed before the barriers: only the atomic round trip is on the critical path
-        int64_t tqs[2] = {sp.tH, sp.tT};
-        int gfs[2], ncs[2], sgfs[2];
-#pragma unroll
-        for (int seg = 0; seg < 2; seg++) {
-            const int64_t gf = sk_owner(tqs[seg] * p.KC, p.C, G), gl = sk_owner((tqs[seg] + 1) * p.KC - 1, p.C, G);
-            gfs[seg] = (int)gf;
-            ncs[seg] = (int)(gl - gf + 1);
-            sgfs[seg] = (sk_begin(gf, p.C, G) == tqs[seg] * p.KC) ? 0 : 1;  // later contributors start inside the tile: slot 0
-        }
-#pragma unroll
-        for (int seg = 0; seg < 2; seg++) {
-            if ((seg == 0 ? sp.nH : sp.nT) == 0) continue;
-            const int64_t tq = tqs[seg];
-            const int gf = gfs[seg], gl = gfs[seg] + ncs[seg] - 1, nc = ncs[seg], sgf = sgfs[seg];
-            named_bar_sync(2 + seg, MV_CONSUMER_WARPS * 32 + 32);  // every consumer warp stored its share of this tile
-            if (p.trace && lane == 0) p.trace[g * 8 + 5] = globaltimer_ns();
-            unsigned int old = 0;
-            if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.ws_cnt + tq) : "memory");
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (p.trace && lane == 0) p.trace[g * 8 + 6] = globaltimer_ns();
-            if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
-            // last arriver: sum the partials in CTA order (deterministic), 4 contributors' loads in flight at a time
-            for (int v = 0; v < 2 * MB; v++) {
-                const int idx = (v * 32 + lane) * 2;  // 128*MB doubles per partial, 2 per lane per pass
-                double2 sum = __ldcg(reinterpret_cast<const double2*>(p.ws_part + ((size_t)gf * 2 + sgf) * (TILE_ROWS * MB) + idx));
-                for (int g0 = gf + 1; g0 <= gl; g0 += 4) {
-                    double2 t4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (g0 + u <= gl) t4[u] = __ldcg(reinterpret_cast<const double2*>(p.ws_part + ((size_t)(g0 + u) * 2) * (TILE_ROWS * MB) + idx));
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (g0 + u <= gl) { sum.x += t4[u].x; sum.y += t4[u].y; }
-                }
-                const double sv[2] = {sum.x, sum.y};
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int rr = (idx + e) / MB, m = (idx + e) % MB;
-                    const int64_t n = tq * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, (float)(sv[e] + (p.bias ? (double)p.bias[n] : 0.0)));
-                }
-            }
-            if (lane == 0) p.ws_cnt[tq] = 0u;
-            if (p.trace && lane == 0) p.trace[g * 8 + 7] = globaltimer_ns();
-        }
-        return;
-    }
-
-    // ===================== consumers =====================
-    pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
-    const int g4 = lane >> 3, i = lane & 7;
-    const FmtMeta meta{p.gpc};
-    // f64 accumulators: every term is an exact product of an f32 scale and an integer partial, so the sum is
-    // independent of the summation order up to 1e-16 -> the result is bit-reproducible against the oracle for any
-    // grid size / stream-K split (oracle orc_matmul_q8).
-    double acc[MV_STEPS][MB];
-#pragma unroll
-    for (int s4 = 0; s4 < MV_STEPS; s4++)
-#pragma unroll
-        for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
-
-    if (PRO) fused_prologue<MB>(p, xhat, tid, warp, lane, g == 0);
-
-    // segment walk: 0 = head (partial, slot 0), 1 = tail (partial, slot 1), 2 = full tiles
-    int kcur = sp.nH > 0 ? sp.kcH : 0;  // k-chunk index of the chunk being processed (fused prologue addressing)
-    int seg = sp.nH > 0 ? 0 : (sp.nT > 0 ? 1 : 2);
-    int seg_left = seg == 0 ? sp.nH : (seg == 1 ? sp.nT : KC);  // chunks until the next flush
-    int t = seg == 0 ? sp.tH : (seg == 1 ? sp.tT : sp.tF);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n_chunks; j++) {
-        mbar_wait(&full[s], ph);
-        if (p.trace && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
-        const uint8_t* wc = stages + (size_t)s * p.stage_bytes;
-        const uint8_t* xr = PRO ? xhat + (size_t)kcur * p.M * ACT_REC_BYTES : wc + p.chunk_bytes;
-        if (PRO) { if (++kcur == KC) kcur = 0; }
-
-        uint4 xa[MB], xb[MB];
-        float dx[MB];
-        int bsA[MB], bsB[MB];
-#pragma unroll
-        for (int m = 0; m < MB; m++) {
-            const uint8_t* rec = xr + m * ACT_REC_BYTES;
-            xa[m] = lds128(rec + 32 * i);
-            xb[m] = lds128(rec + 32 * i + 16);
-            dx[m] = *reinterpret_cast<const float*>(rec + 256 + 4 * i);
-            uint32_t bs = *reinterpret_cast<const uint32_t*>(rec + 288 + 4 * i);
-            bsA[m] = (int)(int16_t)(bs & 0xFFFFu);
-            bsB[m] = (int)(int16_t)(bs >> 16);
-        }
-        if (!(p.debug_flags & 1))
-#pragma unroll
-        for (int s4 = 0; s4 < MV_STEPS; s4++) {
-            const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
-            Unit u;
-            F::template load_unit<true>(wc, r, i, u, meta);
-#pragma unroll
-            for (int m = 0; m < MB; m++) {
-                int sA = 0, sB = 0;
-                sA = __dp4a((int)u.v[0], (int)xa[m].x, sA); sA = __dp4a((int)u.v[1], (int)xa[m].y, sA);
-                sA = __dp4a((int)u.v[2], (int)xa[m].z, sA); sA = __dp4a((int)u.v[3], (int)xa[m].w, sA);
-                sB = __dp4a((int)u.v[4], (int)xb[m].x, sB); sB = __dp4a((int)u.v[5], (int)xb[m].y, sB);
-                sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
-                sA -= u.off[0] * bsA[m];
-                sB -= u.off[1] * bsB[m];
-                double a_ = acc[s4][m];
-                if (F::SUB == 32) {  // one scale per 32 weights
-                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), (double)(sA + sB), a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), (double)(bsA[m] + bsB[m]), a_);
-                } else {             // two 16-wide sub-blocks with their own scales
-                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), (double)sA, a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), (double)bsA[m], a_);
-                    a_ = fma((double)__fmul_rn(u.a[1], dx[m]), (double)sB, a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[1], dx[m]), (double)bsB[m], a_);
-                }
-                acc[s4][m] = a_;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == nst) { s = 0; ph ^= 1u; }
-
-        if (--seg_left > 0) continue;
-
-        // ---- segment / tile boundary: reduce the 8 lanes of each row and flush ----
-#pragma unroll
-        for (int s4 = 0; s4 < MV_STEPS; s4++)
-#pragma unroll
-            for (int m = 0; m < MB; m++) {
-                double v = acc[s4][m];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                acc[s4][m] = v;
-            }
-        if (seg == 2) {
-            if (i == 0) {
-#pragma unroll
-                for (int s4 = 0; s4 < MV_STEPS; s4++) {
-                    const int64_t n = (int64_t)t * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
-                    if (n < p.N) {
-                        const double bv = p.bias ? (double)p.bias[n] : 0.0;
-#pragma unroll
-                        for (int m = 0; m < MB; m++)
-                            if (m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, (float)(acc[s4][m] + bv));
-                    }
-                }
-            }
-        } else {
-            // partial tile: publish my share, then (warp 0) announce the arrival with a release atomic
-            double* part = p.ws_part + ((size_t)g * 2 + seg) * (TILE_ROWS * MB);
-            if (i == 0) {
-#pragma unroll
-                for (int s4 = 0; s4 < MV_STEPS; s4++) {
-                    const int rr = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
-#pragma unroll
-                    for (int m = 0; m < MB; m++) part[rr * MB + m] = acc[s4][m];
-                }
-                __threadfence_block();
-            }
-            __syncwarp();
-            asm volatile("bar.arrive %0, %1;" ::"r"(2 + seg), "r"(MV_CONSUMER_WARPS * 32 + 32) : "memory");
-        }
-#pragma unroll
-        for (int s4 = 0; s4 < MV_STEPS; s4++)
-#pragma unroll
-            for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
-
-        // ---- next segment / tile ----
-        if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; kcur = 0; }
-        else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; kcur = 0; }
-        else { seg_left = KC; t++; }
-
-    }
-    if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
-}
 
 // ------------------------------------------------------------------------------------------------
 // L2 prefetch of the chunks a following matvec launch will stream first.  The matvec CTAs own a whole SM, so
@@ -481,45 +29,16 @@ __global__ void __launch_bounds__(32) l2_prefetch_kernel(const uint8_t* __restri
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------
-template <class F, int MB, bool PRO>
-static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStream_t st) {
-    static bool configured[16] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(MV_THREADS);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap with the predecessor's tail
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO>, p);
-    if (le != cudaSuccess) return le;
-    count_launch();
-    return cudaGetLastError();
-}
 
-template <class F>
-static cudaError_t launch_f(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
-    switch (mb) {
-        case 1: return p.pro ? launch_t<F, 1, true>(p, grid, smem, st) : launch_t<F, 1, false>(p, grid, smem, st);
-        case 2: return p.pro ? launch_t<F, 2, true>(p, grid, smem, st) : launch_t<F, 2, false>(p, grid, smem, st);
-        case 4: return p.pro ? launch_t<F, 4, true>(p, grid, smem, st) : launch_t<F, 4, false>(p, grid, smem, st);
+static cudaError_t launch_family(int family, const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
+    switch (family) {
+        case B200Q_FAM_Q4_K: return mv_launch<B200Q_FAM_Q4_K>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q6_K: return mv_launch<B200Q_FAM_Q6_K>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q8_0: return mv_launch<B200Q_FAM_Q8_0>(p, mb, grid, smem, st);
+        case B200Q_FAM_G4: return mv_launch<B200Q_FAM_G4>(p, mb, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }
-
 static long long* g_trace = nullptr;
 static int g_trace_launch = 0;
 void set_matvec_trace(long long* p) { g_trace = p; g_trace_launch = 0; }
@@ -603,13 +122,7 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
         if (const char* e = getenv("B200Q_MV_L2PF")) p.l2_prefetch_chunks = atoi(e);
     }
     if (const char* e = getenv("B200Q_MV_DEBUG")) p.debug_flags = atoi(e);
-    switch (w->family) {
-        case B200Q_FAM_Q4_K: return launch_f<FmtQ4K>(p, plan.mb, plan.grid, plan.smem_bytes, st);
-        case B200Q_FAM_Q6_K: return launch_f<FmtQ6K>(p, plan.mb, plan.grid, plan.smem_bytes, st);
-        case B200Q_FAM_Q8_0: return launch_f<FmtQ8_0>(p, plan.mb, plan.grid, plan.smem_bytes, st);
-        case B200Q_FAM_G4: return launch_f<FmtG4>(p, plan.mb, plan.grid, plan.smem_bytes, st);
-        default: return cudaErrorInvalidValue;
-    }
+    return launch_family(w->family, p, plan.mb, plan.grid, plan.smem_bytes, st);
 }
 
 }  // namespace b200q
