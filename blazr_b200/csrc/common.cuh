@@ -92,6 +92,13 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ---- named barrier over a subset of the CTA ----
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// unsigned-byte x signed-byte dot product accumulate (dp4a.u32.s32)
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
 // ---- shared memory loads ----
 __device__ __forceinline__ uint4 lds128(const void* p) {
     uint4 v;

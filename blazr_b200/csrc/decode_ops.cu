@@ -109,10 +109,11 @@ __global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restri
 // Two passes with f64 reductions and the deterministic exp, so the result is bit-reproducible against the
 // oracle:  s_j = f32(sum_e q_e k_je) * scale;  p_j = det_exp(s_j - max);  o_e = f32(sum_j p_j v_je) / f32(sum_j p_j).
 // qkv: [M, (nh + 2 nkv) * hd] f32; cache_k/v: [M seqs][max_ctx][nkv][hd] f32; pos[m] = position of the new
-// token; rope: [max_ctx][hd/2][2] (cos, sin).  One CTA of 128 threads per (head, m); dynamic smem = max_ctx f32.
+// token; rope: [max_ctx][hd/2][2] (cos, sin).  One CTA of ATT_NT threads per (head, m); dynamic smem = max_ctx f32.
 // ------------------------------------------------------------------------------------------------
+constexpr int ATT_NT = 512;  // threads per (head, m): 128 positions per score sweep, so a short context is one round trip
 template <int HD>
-__global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos, float* __restrict__ cache_k,
+__global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos, float* __restrict__ cache_k,
                                                            float* __restrict__ cache_v, const float* __restrict__ rope, int nh, int nkv,
                                                            int max_ctx, int M, uint8_t* __restrict__ xq, float* __restrict__ attn_out) {
     pdl_launch_dependents();
@@ -131,8 +132,9 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     const float* rt = rope + (size_t)p * HD;  // [hd/2][2]
 
     __shared__ __align__(16) float sq[HD], sk[HD], sv[HD];
-    __shared__ float s_redf[4];
-    __shared__ double s_redd[4];
+    constexpr int NW = ATT_NT / 32;
+    __shared__ float s_redf[NW];
+    __shared__ double s_redd[NW];
     if (t < HD / 2) {
         const float c = rt[2 * t], sn = rt[2 * t + 1];
         const float q0 = qsrc[2 * t], q1 = qsrc[2 * t + 1];
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     {
         constexpr int QE = HD / 4;  // elements per thread
         const int part = t & 3;
-        for (int j0 = 0; j0 <= p; j0 += 32) {
+        for (int j0 = 0; j0 <= p; j0 += ATT_NT / 4) {
             const int j = j0 + (t >> 2);
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
             if (j <= p) {
@@ -181,9 +183,11 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
     if (lane == 0) s_redf[warp] = lmax;
     __syncthreads();
-    const float gmax = fmaxf(fmaxf(s_redf[0], s_redf[1]), fmaxf(s_redf[2], s_redf[3]));
+    float gmax = s_redf[0];
+#pragma unroll
+    for (int i = 1; i < NW; i++) gmax = fmaxf(gmax, s_redf[i]);
     double lsum = 0.0;
-    for (int j = t; j <= p; j += 128) {
+    for (int j = t; j <= p; j += ATT_NT) {
         const float pj = det_expf(__fsub_rn(s_sc[j], gmax));
         s_sc[j] = pj;
         lsum += (double)pj;
@@ -192,12 +196,15 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
     if (lane == 0) s_redd[warp] = lsum;
     __syncthreads();
-    const float den = (float)(s_redd[0] + s_redd[1] + s_redd[2] + s_redd[3]);
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) dsum += s_redd[i];
+    const float den = (float)dsum;
     // ---- pass 2: thread (eg, jg) accumulates 4 output elements over every 4th position; combine through smem ----
-    __shared__ double s_o[4][HD];
+    constexpr int EG = HD / 4;          // element groups of 4
+    constexpr int JG = ATT_NT / EG;     // position groups (16 for hd 128, 32 for hd 64)
+    __shared__ double s_o[JG][HD];
     {
-        constexpr int EG = HD / 4;          // element groups of 4
-        constexpr int JG = 128 / EG;        // position groups (4 for hd 128, 8 for hd 64)
         const int eg = t % EG, jg = t / EG;
         double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
         for (int j = jg; j <= p; j += JG) {
@@ -206,16 +213,14 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
             o0 = fma((double)pj, (double)vv.x, o0); o1 = fma((double)pj, (double)vv.y, o1);
             o2 = fma((double)pj, (double)vv.z, o2); o3 = fma((double)pj, (double)vv.w, o3);
         }
-        if (jg < 4) { s_o[jg][4 * eg + 0] = o0; s_o[jg][4 * eg + 1] = o1; s_o[jg][4 * eg + 2] = o2; s_o[jg][4 * eg + 3] = o3; }
+        s_o[jg][4 * eg + 0] = o0; s_o[jg][4 * eg + 1] = o1; s_o[jg][4 * eg + 2] = o2; s_o[jg][4 * eg + 3] = o3;
         __syncthreads();
-        if (JG == 8) {  // hd 64: fold the upper four position groups in
-            if (jg >= 4) { s_o[jg - 4][4 * eg + 0] += o0; s_o[jg - 4][4 * eg + 1] += o1; s_o[jg - 4][4 * eg + 2] += o2; s_o[jg - 4][4 * eg + 3] += o3; }
-            __syncthreads();
-        }
     }
     float outv = 0.0f;
     if (t < HD) {
-        const double o = (s_o[0][t] + s_o[1][t]) + (s_o[2][t] + s_o[3][t]);
+        double o = 0.0;
+#pragma unroll
+        for (int i = 0; i < JG; i++) o += s_o[i][t];
         outv = __fdiv_rn((float)o, den);
         if (attn_out) attn_out[(size_t)m * nh * HD + (size_t)head * HD + t] = outv;
         // quantise this head's HD outputs into the o_proj activation records (32-blocks never straddle heads)
@@ -321,11 +326,11 @@ int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, 
     size_t smem = (size_t)max_ctx * sizeof(float);
     if (head_dim == 128) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = launch_pdl(attn_decode_kernel<128>, grid, dim3(128), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
+        e = launch_pdl(attn_decode_kernel<128>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
                        (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out);
     } else if (head_dim == 64) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = launch_pdl(attn_decode_kernel<64>, grid, dim3(128), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
+        e = launch_pdl(attn_decode_kernel<64>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
                        (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out);
     } else {
         return B200Q_ERR_UNSUPPORTED;

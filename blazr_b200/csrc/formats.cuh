@@ -71,6 +71,7 @@ __device__ __forceinline__ void store_nib_unit(uint8_t* dst, const uint8_t* q) {
 // ------------------------------------------------------------------------------------------------
 struct FmtQ4K {
     static constexpr int FAMILY = 1, SUB = 32;
+    static constexpr bool NIB = true;   // 4-bit payload: load_unit<.., RAWHI> available
     static constexpr bool SIGNED = false;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = true;
     static constexpr int QS = 0, HDR = 128 * 128;
@@ -100,12 +101,16 @@ struct FmtQ4K {
             store_nib_unit(qs + 16 * swz8(r, i), v);
         }
     }
-    template <bool SMEM>
+    template <bool SMEM, bool RAWHI = false>
     __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
         uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
         u.v[0] = w.x & 0x0F0F0F0Fu; u.v[1] = w.y & 0x0F0F0F0Fu; u.v[2] = w.z & 0x0F0F0F0Fu; u.v[3] = w.w & 0x0F0F0F0Fu;
-        u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
-        u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        if constexpr (RAWHI) {  // matvec: high nibbles stay in place (16 x value), the integer dot is shifted back once
+            u.v[4] = w.x & 0xF0F0F0F0u; u.v[5] = w.y & 0xF0F0F0F0u; u.v[6] = w.z & 0xF0F0F0F0u; u.v[7] = w.w & 0xF0F0F0F0u;
+        } else {
+            u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
+            u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        }
         const uint8_t* hdr = chunk + HDR + r * 16;
         uint32_t dd = ld4(hdr);
         float d = half_bits_to_float((uint16_t)(dd & 0xFFFF)), dmin = half_bits_to_float((uint16_t)(dd >> 16));
@@ -125,6 +130,7 @@ struct FmtQ4K {
 // ------------------------------------------------------------------------------------------------
 struct FmtQ6K {
     static constexpr int FAMILY = 2, SUB = 16;
+    static constexpr bool NIB = false;
     static constexpr bool SIGNED = false;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = false;
     static constexpr int QL = 0, QH = 128 * 128, SC = QH + 128 * 64, D = SC + 128 * 16;
@@ -166,7 +172,7 @@ struct FmtQ6K {
                 for (int c = 0; c < 4; c++) dst[4 * h + c] = (uint8_t)(w[h] >> (8 * c));
         }
     }
-    template <bool SMEM>
+    template <bool SMEM, bool RAWHI = false>
     __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
         uint4 w = ld16<SMEM>(chunk + QL + r * 128 + 16 * swz8(r, i));
         uint2 hq = ld8<SMEM>(chunk + QH + r * 64 + 16 * swz4(r, i >> 1) + 8 * (i & 1));
@@ -194,6 +200,7 @@ struct FmtQ6K {
 // ------------------------------------------------------------------------------------------------
 struct FmtQ8_0 {
     static constexpr int FAMILY = 3, SUB = 32;
+    static constexpr bool NIB = false;
     static constexpr bool SIGNED = true;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = false;
     static constexpr int QS = 0, D = 128 * 256;
@@ -214,7 +221,7 @@ struct FmtQ8_0 {
             }
         }
     }
-    template <bool SMEM>
+    template <bool SMEM, bool RAWHI = false>
     __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
         uint4 w0 = ld16<SMEM>(chunk + QS + r * 256 + 16 * swz8(r, 2 * i));
         uint4 w1 = ld16<SMEM>(chunk + QS + r * 256 + 16 * swz8(r, 2 * i + 1));
@@ -233,6 +240,7 @@ struct FmtQ8_0 {
 // ------------------------------------------------------------------------------------------------
 struct FmtG4 {
     static constexpr int FAMILY = 4, SUB = 32;
+    static constexpr bool NIB = true;
     static constexpr bool SIGNED = false;  // unit bytes are signed int8 (else unsigned small integers)
     static constexpr bool HAS_MIN = false;
     static constexpr int QS = 0, SC = 128 * 128;
@@ -247,12 +255,16 @@ struct FmtG4 {
         uint8_t* zz = chunk + z_off(gpc) + r * gpc;
         for (int g = 0; g < gpc; g++) { s[2 * g] = (uint8_t)(sc[g] & 0xFF); s[2 * g + 1] = (uint8_t)(sc[g] >> 8); zz[g] = z[g]; }
     }
-    template <bool SMEM>
+    template <bool SMEM, bool RAWHI = false>
     __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta meta) {
         uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
         u.v[0] = w.x & 0x0F0F0F0Fu; u.v[1] = w.y & 0x0F0F0F0Fu; u.v[2] = w.z & 0x0F0F0F0Fu; u.v[3] = w.w & 0x0F0F0F0Fu;
-        u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
-        u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        if constexpr (RAWHI) {  // matvec: high nibbles stay in place (16 x value), the integer dot is shifted back once
+            u.v[4] = w.x & 0xF0F0F0F0u; u.v[5] = w.y & 0xF0F0F0F0u; u.v[6] = w.z & 0xF0F0F0F0u; u.v[7] = w.w & 0xF0F0F0F0u;
+        } else {
+            u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
+            u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        }
         int gq = (i * meta.gpc) >> 3;
         float s = half_bits_to_float(ld2(chunk + SC + (r * meta.gpc + gq) * 2));
         int z = chunk[z_off(meta.gpc) + r * meta.gpc + gq];

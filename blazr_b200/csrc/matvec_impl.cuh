@@ -128,7 +128,7 @@ __device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* x
 }
 
 template <class F, int MB, bool PRO>
-__global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParams p) {
+__global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + MV_MAX_STAGES;
@@ -237,20 +237,32 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
             old = __shfl_sync(0xffffffffu, old, 0);
             if (p.trace && lane == 0) p.trace[g * 8 + 6] = globaltimer_ns();
             if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
-            // last arriver: sum the partials in CTA order (deterministic), 4 contributors' loads in flight at a time
-            for (int v = 0; v < 2 * MB; v++) {
-                const int idx = (v * 32 + lane) * 2;  // 128*MB doubles per partial, 2 per lane per pass
-                double2 sum = __ldcg(reinterpret_cast<const double2*>(p.ws_part + ((size_t)gf * 2 + sgf) * (TILE_ROWS * MB) + idx));
-                for (int g0 = gf + 1; g0 <= gl; g0 += 4) {
-                    double2 t4[4];
+            // last arriver: sum the partials in CTA order (deterministic).  Every load of a batch of NB contributors
+            // x all passes is issued before the first add, so the reduction costs one L2 round trip per NB contributors.
+            constexpr int PASSES = 2 * MB;                       // 64 doubles (one double2 per lane) per pass
+            constexpr int NB = MB == 1 ? 8 : (MB == 2 ? 4 : 2);  // contributors in flight
+            double2 sum[PASSES];
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (g0 + u <= gl) t4[u] = __ldcg(reinterpret_cast<const double2*>(p.ws_part + ((size_t)(g0 + u) * 2) * (TILE_ROWS * MB) + idx));
+            for (int v = 0; v < PASSES; v++) sum[v] = make_double2(0.0, 0.0);
+            for (int g0 = gf; g0 <= gl; g0 += NB) {
+                double2 tb[NB][PASSES];
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (g0 + u <= gl) { sum.x += t4[u].x; sum.y += t4[u].y; }
+                for (int u = 0; u < NB; u++) {
+                    const int gg = g0 + u;
+                    const double* src = p.ws_part + ((size_t)gg * 2 + (gg == gf ? sgf : 0)) * (TILE_ROWS * MB) + lane * 2;
+#pragma unroll
+                    for (int v = 0; v < PASSES; v++)
+                        tb[u][v] = (gg <= gl) ? __ldcg(reinterpret_cast<const double2*>(src + v * 64)) : make_double2(0.0, 0.0);
                 }
-                const double sv[2] = {sum.x, sum.y};
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+#pragma unroll
+                    for (int v = 0; v < PASSES; v++) { sum[v].x += tb[u][v].x; sum[v].y += tb[u][v].y; }
+            }
+#pragma unroll
+            for (int v = 0; v < PASSES; v++) {
+                const int idx = (v * 32 + lane) * 2;
+                const double sv[2] = {sum[v].x, sum[v].y};
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
@@ -311,14 +323,20 @@ __global__ void __launch_bounds__(MV_THREADS, 2) matvec_kernel(const MatvecParam
         for (int s4 = 0; s4 < MV_STEPS; s4++) {
             const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
             Unit u;
-            F::template load_unit<true>(wc, r, i, u, meta);
+            F::template load_unit<true, F::NIB>(wc, r, i, u, meta);
 #pragma unroll
             for (int m = 0; m < MB; m++) {
                 int sA = 0, sB = 0;
                 sA = __dp4a((int)u.v[0], (int)xa[m].x, sA); sA = __dp4a((int)u.v[1], (int)xa[m].y, sA);
                 sA = __dp4a((int)u.v[2], (int)xa[m].z, sA); sA = __dp4a((int)u.v[3], (int)xa[m].w, sA);
-                sB = __dp4a((int)u.v[4], (int)xb[m].x, sB); sB = __dp4a((int)u.v[5], (int)xb[m].y, sB);
-                sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
+                if constexpr (F::NIB) {  // bytes hold 16 x q (unsigned): exact u8 x s8 dot, one arithmetic shift back
+                    sB = dp4a_us(u.v[4], xb[m].x, sB); sB = dp4a_us(u.v[5], xb[m].y, sB);
+                    sB = dp4a_us(u.v[6], xb[m].z, sB); sB = dp4a_us(u.v[7], xb[m].w, sB);
+                    sB >>= 4;
+                } else {
+                    sB = __dp4a((int)u.v[4], (int)xb[m].x, sB); sB = __dp4a((int)u.v[5], (int)xb[m].y, sB);
+                    sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
+                }
                 sA -= u.off[0] * bsA[m];
                 sB -= u.off[1] * bsB[m];
                 double a_ = acc[s4][m];
