@@ -49,22 +49,30 @@ static cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, size
 
 // ------------------------------------------------------------------------------------------------
 // h_out = h_in (+ delta) ; xq = quant(rmsnorm(h_out) * w)
-// One CTA of 256 threads per (256-k chunk, token row): every CTA recomputes the row's sum of squares (the row
+// One CTA of NORM_NT threads per (256-k chunk, token row): every CTA recomputes the row's sum of squares (the row
 // is 8-32 KB and L2 resident) and then normalises / quantises / writes only its own chunk, so the operator
 // runs H/256 CTAs wide instead of one.  h_in and h_out must be different buffers when delta != null.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(const float* __restrict__ h_in, const float* __restrict__ delta,
-                                                                 float* __restrict__ h_out, const float* __restrict__ w, float eps, int H, int M,
-                                                                 uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
+constexpr int NORM_NT = 1024;  // one float4 of the row per thread for H = 4096: the whole row is one load round trip
+__global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float* __restrict__ h_in, const float* __restrict__ delta,
+                                                                     float* __restrict__ h_out, const float* __restrict__ w, float eps, int H, int M,
+                                                                     uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
     pdl_launch_dependents();
-    pdl_wait();
     const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
     const float* hr = h_in + (size_t)m * H;
     const float* dr = delta ? delta + (size_t)m * H : nullptr;
-    __shared__ double red[8];
+    __shared__ double red[NORM_NT / 32];
+    const float wk = (t < CHUNK_K) ? w[kc * CHUNK_K + t] : 0.0f;  // static weights: fetched before the dependency wait
+    pdl_wait();
     // f64: exact squares, order-independent sum -> bit-reproducible against the oracle (4 independent chains)
+    float mine = 0.0f;
+    if (t < CHUNK_K) {
+        mine = hr[kc * CHUNK_K + t];
+        if (dr) mine = __fadd_rn(mine, dr[kc * CHUNK_K + t]);
+    }
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int k4 = t; k4 < H / 4; k4 += 256) {
+#pragma unroll 2
+    for (int k4 = t; k4 < H / 4; k4 += NORM_NT) {
         float4 v = reinterpret_cast<const float4*>(hr)[k4];
         if (dr) {
             const float4 d4 = reinterpret_cast<const float4*>(dr)[k4];
@@ -74,19 +82,18 @@ __global__ void __launch_bounds__(256) add_rmsnorm_quant_kernel(const float* __r
         s2 = fma((double)v.z, (double)v.z, s2); s3 = fma((double)v.w, (double)v.w, s3);
     }
     double ss = (s0 + s1) + (s2 + s3);
-    float mine = hr[kc * CHUNK_K + t];
-    if (dr) mine = __fadd_rn(mine, dr[kc * CHUNK_K + t]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((t & 31) == 0) red[t >> 5] = ss;
     __syncthreads();
+    if (t >= CHUNK_K) return;
     double tot = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) tot += red[i];
+    for (int i = 0; i < NORM_NT / 32; i++) tot += red[i];
     const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)H), eps)));
     const int k = kc * CHUNK_K + t;
     h_out[(size_t)m * H + k] = mine;
-    const float v = __fmul_rn(__fmul_rn(mine, inv), w[k]);
+    const float v = __fmul_rn(__fmul_rn(mine, inv), wk);
     if (xnorm) xnorm[(size_t)m * H + k] = v;
     quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
 }
@@ -117,7 +124,6 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
                                                            float* __restrict__ cache_v, const float* __restrict__ rope, int nh, int nkv,
                                                            int max_ctx, int M, uint8_t* __restrict__ xq, float* __restrict__ attn_out) {
     pdl_launch_dependents();
-    pdl_wait();
     extern __shared__ float s_sc[];  // scores, then probabilities, for positions 0..p
     const int head = blockIdx.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int kvh = head / (nh / nkv);
@@ -135,8 +141,33 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
     constexpr int NW = ATT_NT / 32;
     __shared__ float s_redf[NW];
     __shared__ double s_redd[NW];
+    // ---- before griddepcontrol.wait: everything that does not depend on the qkv matvec running just ahead of this
+    // kernel -- pos (advanced by the previous step's argmax), the RoPE row and the cached K / V rows j < p (written by
+    // earlier steps) -- is pulled into registers, so only the new q/k/v load remains on the critical path after it.
+    constexpr int QE = HD / 4;          // score pass: elements per thread (4 threads per position)
+    constexpr int EG = HD / 4;          // output pass: element groups of 4
+    constexpr int JG = ATT_NT / EG;     // output pass: position groups (16 for hd 128, 32 for hd 64)
+    constexpr int VPF = 8;              // prefetched output-pass iterations (positions < VPF * JG)
+    const int part = t & 3;
+    const int eg = t % EG, jg = t / EG;
+    float4 kpre[QE / 4], vpre[VPF];
+    float rc = 0.0f, rs = 0.0f;
+    {
+        const int j = t >> 2;
+        if (j < p) {
+#pragma unroll
+            for (int e = 0; e < QE / 4; e++) kpre[e] = *reinterpret_cast<const float4*>(ck + (size_t)j * pstride + part * QE + 4 * e);
+        }
+#pragma unroll
+        for (int it = 0; it < VPF; it++) {
+            const int jv = jg + it * JG;
+            if (jv < p) vpre[it] = *reinterpret_cast<const float4*>(cv + (size_t)jv * pstride + 4 * eg);
+        }
+        if (t < HD / 2) { rc = rt[2 * t]; rs = rt[2 * t + 1]; }
+    }
+    pdl_wait();
     if (t < HD / 2) {
-        const float c = rt[2 * t], sn = rt[2 * t + 1];
+        const float c = rc, sn = rs;
         const float q0 = qsrc[2 * t], q1 = qsrc[2 * t + 1];
         sq[2 * t] = __fsub_rn(__fmul_rn(q0, c), __fmul_rn(q1, sn));
         sq[2 * t + 1] = __fadd_rn(__fmul_rn(q0, sn), __fmul_rn(q1, c));
@@ -154,8 +185,6 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
     float lmax = -INFINITY;
     {
-        constexpr int QE = HD / 4;  // elements per thread
-        const int part = t & 3;
         for (int j0 = 0; j0 <= p; j0 += ATT_NT / 4) {
             const int j = j0 + (t >> 2);
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
@@ -164,7 +193,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
                 const float* qq = sq + part * QE;
 #pragma unroll
                 for (int e = 0; e < QE; e += 4) {
-                    const float4 kk = *reinterpret_cast<const float4*>(kr + e);
+                    const float4 kk = (j0 == 0 && j < p) ? kpre[e / 4] : *reinterpret_cast<const float4*>(kr + e);
                     d0 = fma((double)qq[e + 0], (double)kk.x, d0); d1 = fma((double)qq[e + 1], (double)kk.y, d1);
                     d2 = fma((double)qq[e + 2], (double)kk.z, d2); d3 = fma((double)qq[e + 3], (double)kk.w, d3);
                 }
@@ -201,13 +230,20 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
     for (int i = 0; i < NW; i++) dsum += s_redd[i];
     const float den = (float)dsum;
     // ---- pass 2: thread (eg, jg) accumulates 4 output elements over every 4th position; combine through smem ----
-    constexpr int EG = HD / 4;          // element groups of 4
-    constexpr int JG = ATT_NT / EG;     // position groups (16 for hd 128, 32 for hd 64)
     __shared__ double s_o[JG][HD];
     {
-        const int eg = t % EG, jg = t / EG;
         double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
-        for (int j = jg; j <= p; j += JG) {
+#pragma unroll
+        for (int it = 0; it < VPF; it++) {  // prefetched rows (and the new token's row when it falls in this range)
+            const int j = jg + it * JG;
+            if (j <= p) {
+                const float pj = s_sc[j];
+                const float4 vv = (j < p) ? vpre[it] : *reinterpret_cast<const float4*>(sv + 4 * eg);
+                o0 = fma((double)pj, (double)vv.x, o0); o1 = fma((double)pj, (double)vv.y, o1);
+                o2 = fma((double)pj, (double)vv.z, o2); o3 = fma((double)pj, (double)vv.w, o3);
+            }
+        }
+        for (int j = jg + VPF * JG; j <= p; j += JG) {
             const float pj = s_sc[j];
             const float4 vv = (j < p) ? *reinterpret_cast<const float4*>(cv + (size_t)j * pstride + 4 * eg) : *reinterpret_cast<const float4*>(sv + 4 * eg);
             o0 = fma((double)pj, (double)vv.x, o0); o1 = fma((double)pj, (double)vv.y, o1);
@@ -303,7 +339,7 @@ int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_
                                 float* xnorm, void* stream) {
     if (!h_in || !h_out || !w || !xq || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
     if (delta && h_in == h_out) return B200Q_ERR_INVALID_ARG;  // CTAs re-read the whole input row: no in-place update
-    cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)(H / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, h_in, delta,
+    cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)(H / CHUNK_K), (unsigned)M), dim3(NORM_NT), 0, (cudaStream_t)stream, h_in, delta,
                                h_out, w, eps, (int)H, (int)M, (uint8_t*)xq, xnorm);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }
