@@ -353,6 +353,76 @@ int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* 
     return B200Q_OK;
 }
 
+// ---- expert banks (MoE) ----
+int32_t b200q_bank_create(const b200q_weight* const* experts, int32_t E, b200q_bank** out) {
+    if (!experts || !out || E < 1) return fail(B200Q_ERR_INVALID_ARG, "bad bank arguments");
+    const b200q_weight* w0 = experts[0];
+    if (!w0) return fail(B200Q_ERR_INVALID_ARG, "null expert 0");
+    for (int e = 0; e < E; e++) {
+        const b200q_weight* w = experts[e];
+        if (!w) return fail(B200Q_ERR_INVALID_ARG, "null expert %d", e);
+        if (w->family != w0->family || w->N != w0->N || w->K != w0->K || w->chunk_bytes != w0->chunk_bytes || w->gpc != w0->gpc || w->device != w0->device)
+            return fail(B200Q_ERR_INVALID_ARG, "expert %d differs from expert 0 in format, shape or device", e);
+        if (w->bias || w->perm) return fail(B200Q_ERR_UNSUPPORTED, "bank members must not carry a bias or an act-order permutation");
+    }
+    b200q_bank* b = new b200q_bank();
+    b->E = E;
+    b->proto = *w0;
+    b->proto.data = nullptr;
+    b->members = new const b200q_weight*[E];
+    std::vector<const uint8_t*> tab(E);
+    for (int e = 0; e < E; e++) { b->members[e] = experts[e]; tab[e] = experts[e]->data; }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(w0->device);
+    cudaError_t ce = cudaMalloc((void**)&b->table_dev, sizeof(uint8_t*) * (size_t)E);
+    if (ce == cudaSuccess) ce = cudaMemcpy((void*)b->table_dev, tab.data(), sizeof(uint8_t*) * (size_t)E, cudaMemcpyHostToDevice);
+    cudaSetDevice(prev);
+    if (ce != cudaSuccess) { delete[] b->members; delete b; return cuda_fail(ce, "bank table upload"); }
+    *out = b;
+    return B200Q_OK;
+}
+
+int32_t b200q_bank_free(b200q_bank* b) {
+    if (!b) return B200Q_OK;
+    if (b->table_dev) cudaFree((void*)b->table_dev);
+    delete[] b->members;
+    delete b;
+    return B200Q_OK;
+}
+
+int32_t b200q_bank_set(b200q_bank* b, int32_t e, const b200q_weight* w, void* stream) {
+    if (!b || !w || e < 0 || e >= b->E) return fail(B200Q_ERR_INVALID_ARG, "bad bank_set arguments");
+    const b200q_weight& p0 = b->proto;
+    if (w->family != p0.family || w->N != p0.N || w->K != p0.K || w->chunk_bytes != p0.chunk_bytes || w->gpc != p0.gpc || w->device != p0.device || w->bias || w->perm)
+        return fail(B200Q_ERR_INVALID_ARG, "replacement expert differs from the bank's format, shape or device");
+    b->members[e] = w;
+    CUDA_TRY(cudaMemcpyAsync((void*)(b->table_dev + e), &w->data, sizeof(uint8_t*), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));  // &w->data is host stack/heap memory: finish before returning
+    return B200Q_OK;
+}
+
+const b200q_weight* b200q_bank_get(const b200q_bank* b, int32_t e) {
+    if (!b || e < 0 || e >= b->E) return nullptr;
+    return b->members[e];
+}
+
+size_t b200q_bank_workspace_bytes(const b200q_bank* b, int64_t n_slots) {
+    if (!b || n_slots < 1) return 0;
+    return align256(matvec_grouped_ws_bytes(b, n_slots));
+}
+
+int32_t b200q_moe_matmul_q8(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const void* xq, int64_t x_rows, int64_t x_slot_div, void* y,
+                            int32_t y_dtype, int64_t y_slot_stride, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!b || !sel_dev || !xq || !y || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+    if (n_slots < 1 || n_slots > 65536) return fail(B200Q_ERR_INVALID_ARG, "n_slots out of range");
+    if (x_slot_div < 1 || x_rows < 1 || (n_slots + x_slot_div - 1) / x_slot_div > x_rows) return fail(B200Q_ERR_INVALID_ARG, "activation rows do not cover the slots");
+    if (y_slot_stride < b->proto.N || y_dtype < 0 || y_dtype > 2) return fail(B200Q_ERR_INVALID_ARG, "bad y_slot_stride / y_dtype");
+    if (workspace_bytes < b200q_bank_workspace_bytes(b, n_slots)) return fail(B200Q_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, b200q_bank_workspace_bytes(b, n_slots));
+    CUDA_TRY(launch_matvec_grouped(b, sel_dev, n_slots, (const uint8_t*)xq, x_rows, x_slot_div, y, y_dtype, y_slot_stride, (uint8_t*)workspace, (cudaStream_t)stream));
+    return B200Q_OK;
+}
+
 int32_t b200q_matmul_path(const b200q_weight* w, int32_t path, const void* x, int32_t x_dtype, int64_t M, int64_t ldx, void* y,
                           int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
     if (!w || !x || !y || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");

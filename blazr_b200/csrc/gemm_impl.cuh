@@ -21,8 +21,9 @@
 namespace b200q {
 
 
-constexpr int GT_DQ_WARPS = 8;                     // dequant warps: 2 per TMEM lane quarter, each half of the chunk's k (16 warps measured slower)
-constexpr int GT_THREADS = (4 + GT_DQ_WARPS) * 32;
+// dequant warps (template parameter DQW): DQW/4 per TMEM lane quarter, each 4/DQW of the chunk's k.  8 for wide M tiles
+// (the MMA is the bottleneck; 16 measured slower there), 16 for skinny M (<= 64), where every weight is expanded for a
+// handful of MMAs and the expansion's latency chains are what bounds the kernel (ncu r1: 2 warps/scheduler, IPC 0.4).
 constexpr int GT_NX = 16;      // max activation sub-stage ring depth (64 k each); runtime depth p.nx
 constexpr int GT_ASLOTS = 3;   // max TMEM A slots; one slot = one whole 256-k chunk of f16 (128 columns)
 constexpr int GT_MAX_NW = 4;   // weight chunk ring
@@ -40,6 +41,7 @@ struct GemmParams {
     int T, KC, MT, Mt;
     int gpc, chunk_bytes, nw, w_stage_bytes, x_stage_bytes;
     int nslots, a_col, nx;
+    int dq_warps;      // 8 (wide M tiles) or 16 + dedicated epilogue warps + two accumulators (Mt <= 128)
     int splits;        // split-K factor (serial K loop is the latency floor when there are fewer tiles than SMs)
     float* partial;    // [splits][M][N] f32 when splits > 1
     uint32_t idesc;
@@ -90,7 +92,7 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
 
 // 32 integer weights of a unit (one byte each) -> 16 packed f16 pairs  w = a*(v-off) - b,  rounded once to f16.
 // Bytes become f16 with the 0x6400 trick (0x6400 | v == 1024 + v exactly), the integer offset is removed with an
-// exact HSUB2 and the scale/min applied with one HFMA2: ~1.75 instructions per weight, no I2F, no PRMT.
+// exact HSUB2 and the scale/min applied with one HFMA2: one PRMT + HSUB2 + HFMA2 per pair of weights, no I2F.
 // Pair order: word k yields (e0,e2) then (e1,e3) -- the activation staging kernel applies the same [0,2,1,3]
 // permutation inside every group of 4 k, so the contraction is unchanged.
 template <bool SIGNED>
@@ -104,8 +106,8 @@ __device__ __forceinline__ void unit_to_f16(const Unit& u, uint32_t* out) {
 #pragma unroll
         for (int k = 4 * h; k < 4 * h + 4; k++) {
             const uint32_t wv = SIGNED ? (u.v[k] ^ 0x80808080u) : u.v[k];
-            uint32_t p02 = (wv & 0x00FF00FFu) | 0x64006400u;          // (1024 + e0, 1024 + e2)
-            uint32_t p13 = ((wv >> 8) & 0x00FF00FFu) | 0x64006400u;   // (1024 + e1, 1024 + e3)
+            uint32_t p02 = __byte_perm(wv, 0x64646464u, 0x4240);      // bytes [e0, 0x64, e2, 0x64] = (1024 + e0, 1024 + e2): one PRMT
+            uint32_t p13 = __byte_perm(wv, 0x64646464u, 0x4341);      // (1024 + e1, 1024 + e3)
             __half2 x02 = __hsub2(*reinterpret_cast<__half2*>(&p02), off2);
             __half2 x13 = __hsub2(*reinterpret_cast<__half2*>(&p13), off2);
             x02 = __hfma2(x02, a2, nb2);
@@ -116,8 +118,13 @@ __device__ __forceinline__ void unit_to_f16(const Unit& u, uint32_t* out) {
     }
 }
 
-template <class F>
-__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+// EPI: four dedicated epilogue warps (one per TMEM lane quarter) and two accumulator buffers (Mt <= 128), so the
+// dequant warps start the next work item while the previous accumulator drains -- skinny launches are made of many
+// short items and the drain (MMA latency + tcgen05.ld + global stores) otherwise sits between every pair of them.
+template <class F, int DQW, bool EPI>
+__global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_kernel(const GemmParams p) {
+    constexpr int GT_DQ_WARPS = DQW;
+    constexpr int KG = DQW / 4;        // k groups: warp (q, h) expands units KG*j + h, j < 8 / KG
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_w = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_w = full_w + GT_MAX_NW;
@@ -125,8 +132,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
     uint64_t* empty_x = full_x + GT_NX;
     uint64_t* a_full = empty_x + GT_NX;
     uint64_t* a_empty = a_full + GT_ASLOTS;
-    uint64_t* d_full = a_empty + GT_ASLOTS;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_full + 1);
+    uint64_t* d_full = a_empty + GT_ASLOTS;   // [2]
+    uint64_t* d_empty = d_full + 2;           // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
     uint8_t* xst = smem + GT_HDR;
     uint8_t* wst = xst + (size_t)p.nx * p.x_stage_bytes;
 
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
         for (int s = 0; s < p.nw; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], GT_DQ_WARPS); }
         for (int s = 0; s < p.nx; s++) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
         for (int s = 0; s < p.nslots; s++) { mbar_init(&a_full[s], GT_DQ_WARPS); mbar_init(&a_empty[s], 1); }
-        mbar_init(d_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -192,11 +200,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
     } else if (warp == 1) {
         // ===================== single-thread MMA issuer =====================
         if (lane == 0) {
-            int xs = 0, as = 0;
-            uint32_t xph = 0, aph = 0;
+            int xs = 0, as = 0, acc = 0;
+            uint32_t xph = 0, aph = 0, eph0 = 1, eph1 = 1;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int sp_ = tile % p.splits;
                 const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                if (EPI) {  // the epilogue warps have drained this accumulator buffer (two items ago)
+                    mbar_wait(&d_empty[acc], acc ? eph1 : eph0);
+                    if (acc) eph1 ^= 1u; else eph0 ^= 1u;
+                    tc_fence_after();
+                }
+                const uint32_t d_col = GT_D_COL + (EPI ? acc * p.Mt : 0);
                 for (int kc = kc0; kc < kc1; kc++) {
                     mbar_wait(&a_full[as], aph);  // a whole dequantised chunk (4 x 64 k) is in TMEM
                     const uint32_t a_chunk = tmem + p.a_col + as * 128;
@@ -207,19 +221,56 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
                         const uint64_t bdesc = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
 #pragma unroll
                         for (int kk = 0; kk < 4; kk++)
-                            tc_mma_ts(tmem + GT_D_COL, a_chunk + j * 32 + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
+                            tc_mma_ts(tmem + d_col, a_chunk + j * 32 + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
                         tc_commit(&empty_x[xs]);
                         if (++xs == p.nx) { xs = 0; xph ^= 1u; }
                     }
                     tc_commit(&a_empty[as]);
                     if (++as == p.nslots) { as = 0; aph ^= 1u; }
                 }
-                tc_commit(d_full);
+                tc_commit(&d_full[acc]);
+                if (EPI) acc ^= 1;
             }
+        }
+    } else if (EPI && warp >= 4 + DQW) {
+        // ===================== dedicated epilogue warps: accumulator rows = n, columns = m =====================
+        const int q = warp & 3;
+        const int r = 32 * q + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
+        int acc = 0;
+        uint32_t ph0 = 0, ph1 = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int sp_ = tile % p.splits, t = (tile / p.splits) / p.MT, mt = (tile / p.splits) % p.MT;
+            mbar_wait(&d_full[acc], acc ? ph1 : ph0);
+            if (acc) ph1 ^= 1u; else ph0 ^= 1u;
+            tc_fence_after();
+            const int64_t n = (int64_t)t * TILE_ROWS + r;
+            const float bv = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
+            for (int cb = 0; cb < p.Mt; cb += 16) {
+                uint32_t v[16];
+                tc_ld16(lane_base + GT_D_COL + acc * p.Mt + cb, v);
+                tc_wait_ld();
+                if (cb + 16 >= p.Mt) {  // last read of this buffer: hand it back to the MMA issuer before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[acc]);
+                }
+                if (n < p.N) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) {
+                        const int64_t m = (int64_t)mt * p.Mt + cb + c;
+                        if (m < p.M) {
+                            if (p.splits > 1) p.partial[((size_t)sp_ * p.M + m) * p.N + n] = __uint_as_float(v[c]);
+                            else store_out(p.y, p.y_dtype, m * p.ldy + n, __uint_as_float(v[c]) + bv);
+                        }
+                    }
+                }
+            }
+            acc ^= 1;
         }
     } else if (warp >= 4) {
         // ===================== dequant (thread == weight row) + epilogue =====================
-        const int q = warp & 3, h = (warp - 4) >> 2;  // lane quarter; k half (units 2j+h) and epilogue column half
+        const int q = warp & 3, h = (warp - 4) >> 2;  // lane quarter; k group (units KG*j+h); h < 2 also = epilogue column half
         const int r = 32 * q + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
         const FmtMeta meta{p.gpc};
@@ -234,12 +285,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
                 mbar_wait(&a_empty[as], aph);  // the MMAs that read this TMEM slot two/three chunks ago are done
                 tc_fence_after();
 #pragma unroll 1
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < 8 / KG; j++) {
                     Unit u;
-                    F::template load_unit<true>(wc, r, 2 * j + h, u, meta);
+                    F::template load_unit<true>(wc, r, KG * j + h, u, meta);
                     uint32_t pk[16];
                     unit_to_f16<F::SIGNED>(u, pk);
-                    tc_st16(lane_base + p.a_col + as * 128 + j * 32 + 16 * h, pk);
+                    tc_st16(lane_base + p.a_col + as * 128 + (KG * j + h) * 16, pk);
                 }
                 tc_wait_st();
                 tc_fence_before();
@@ -250,8 +301,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
                 if (lane == 0) mbar_arrive(&empty_w[ws]);
                 if (++ws == p.nw) { ws = 0; wph ^= 1u; }
             }
+            if (EPI) continue;  // the dedicated epilogue warps drain the accumulator
             // ---- epilogue: accumulator rows = n, columns = m ----
-            mbar_wait(d_full, dph);
+            mbar_wait(&d_full[0], dph);
             dph ^= 1u;
             tc_fence_after();
             const int64_t n = (int64_t)t * TILE_ROWS + r;
@@ -284,19 +336,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmParams
     }
 }
 
-template <class F>
-static cudaError_t launch_gemm_t(const GemmParams& p, int grid, int smem, cudaStream_t st) {
+template <class F, int DQW, bool EPI>
+static cudaError_t launch_gemm_dq(const GemmParams& p, int grid, int smem, cudaStream_t st) {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F, DQW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    gemm_tc_kernel<F><<<grid, GT_THREADS, smem, st>>>(p);
+    gemm_tc_kernel<F, DQW, EPI><<<grid, (4 + DQW + (EPI ? 4 : 0)) * 32, smem, st>>>(p);
     count_launch();
     return cudaGetLastError();
+}
+template <class F>
+static cudaError_t launch_gemm_t(const GemmParams& p, int grid, int smem, cudaStream_t st) {
+    return p.dq_warps == 16 ? launch_gemm_dq<F, 16, true>(p, grid, smem, st) : launch_gemm_dq<F, 8, false>(p, grid, smem, st);
 }
 
 

@@ -34,12 +34,30 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
     store_out(y, y_dtype, m * ldy + n, acc + (bias ? bias[n] : 0.0f));
 }
 
-static int pick_splits(const b200q_weight* w, int MT) {
-    int64_t tiles = w->T * MT;
-    int s = (int)(w->num_sms / tiles);
-    if (s > 8) s = 8;
-    if (s > (int)w->KC) s = (int)w->KC;
-    return s < 1 ? 1 : s;
+// split-K factor: the work items (tiles x splits) should fill whole waves of the SMs.  Wide-M launches only split
+// when there are fewer tiles than SMs; skinny launches (one M tile, HBM-bound) pick the split with the least wave
+// quantisation loss, since a 112-tile weight on 148 SMs otherwise idles a quarter of the machine.
+static int pick_splits(const b200q_weight* w, int MT, int64_t M) {
+    const int64_t tiles = w->T * MT;
+    const int sms = w->num_sms;
+    int smax = 8;
+    if (smax > (int)w->KC / 2) smax = (int)w->KC / 2;
+    if (smax < 1) smax = 1;
+    if (M > 128) {
+        int s = (int)(sms / tiles);
+        if (s > smax) s = smax;
+        return s < 1 ? 1 : s;
+    }
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= smax; s++) {
+        const int64_t items = tiles * s;
+        const int64_t waves = (items + sms - 1) / sms;
+        double eff = (double)items / (double)(waves * sms);
+        eff -= 0.01 * (s - 1);  // partial-sum traffic and a shorter K loop per item
+        if (eff > best_eff) { best_eff = eff; best = s; }
+    }
+    return best;
 }
 
 static int pick_mt(int64_t M, int* MT) {
@@ -55,7 +73,7 @@ size_t gemm_ws_bytes(const b200q_weight* w, int64_t M) {
     int MT;
     int Mt = pick_mt(M, &MT);
     size_t xs = ((size_t)MT * Mt * (size_t)w->K_pad * 2 + 255) & ~(size_t)255;
-    int S = pick_splits(w, MT);
+    int S = pick_splits(w, MT, M);
     return xs + (S > 1 ? (size_t)S * M * w->N * sizeof(float) : 0);
 }
 
@@ -113,11 +131,12 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     if (nw > GT_MAX_NW) nw = GT_MAX_NW;
     if (nw < 2) return cudaErrorNotSupported;
     p.nw = nw;
-    p.nslots = Mt > 128 ? 2 : 3;
+    p.nslots = Mt > 64 ? 2 : 3;   // TMEM: 2 accumulators x Mt (Mt <= 128) or one of 256 columns, A slots of 128 columns on top
     p.a_col = 512 - 128 * p.nslots;
     p.idesc = (1u << 4) | ((uint32_t)(Mt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major A/B, M=128, N=Mt
     int smem = GT_HDR + nx * p.x_stage_bytes + nw * p.w_stage_bytes;
-    p.splits = pick_splits(w, MT);
+    p.splits = pick_splits(w, MT, M);
+    p.dq_warps = Mt <= 128 ? 16 : 8;
     p.partial = reinterpret_cast<float*>(ws + (((size_t)MT * Mt * (size_t)w->K_pad * 2 + 255) & ~(size_t)255));
     int64_t tiles = (int64_t)p.T * MT * p.splits;
     int grid = (int)(tiles < w->num_sms ? tiles : w->num_sms);

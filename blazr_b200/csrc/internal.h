@@ -18,6 +18,15 @@ struct b200q_weight {
     int num_sms;
 };
 
+// Expert bank (boostr::ExpertWeights stacked [num_experts, ...]): E weights of one format and shape
+// addressed through a device-resident pointer table, so one grouped launch streams the selected experts.
+struct b200q_bank {
+    int E;
+    b200q_weight proto;              // shape / format of every member (data = null)
+    const uint8_t** table_dev;       // device array [E] of repacked weight buffers
+    const b200q_weight** members;    // host array [E] (not owned)
+};
+
 namespace b200q {
 
 void count_launch(int n = 1);
@@ -56,6 +65,9 @@ void set_matvec_trace(long long* dev_buf);
 cudaError_t launch_l2_prefetch(const b200q_weight* w, int64_t M, int64_t max_bytes, cudaStream_t st);
 cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
                           const FusedPrologue* fp = nullptr);
+size_t matvec_grouped_ws_bytes(const b200q_bank* b, int64_t n_slots);
+cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const uint8_t* xq, int64_t x_rows, int64_t x_slot_div,
+                                  void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st);
 
 // ---- gemm_tc.cu ----
 size_t gemm_ws_bytes(const b200q_weight* w, int64_t M);

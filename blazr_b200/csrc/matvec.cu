@@ -112,6 +112,12 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.norm_w = fp ? fp->norm_w : nullptr;
     p.eps = fp ? fp->eps : 0.0f;
     p.gate_up = fp ? fp->gate_up : nullptr;
+    p.w_table = nullptr;
+    p.sel = nullptr;
+    p.tpw = (int)w->T;
+    p.x_rows = (int)M;
+    p.x_slot_div = 1;
+    p.y_slot_stride = 0;
     p.trace = g_trace ? g_trace + (size_t)(g_trace_launch++) * 148 * 8 : nullptr;
     p.debug_flags = 0;
     {
@@ -123,6 +129,48 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     }
     if (const char* e = getenv("B200Q_MV_DEBUG")) p.debug_flags = atoi(e);
     return launch_family(w->family, p, plan.mb, plan.grid, plan.smem_bytes, st);
+}
+
+// ---- grouped launch over an expert bank: n_slots independent M = 1 matvecs in one stream-K grid ----
+size_t matvec_grouped_ws_bytes(const b200q_bank* b, int64_t n_slots) {
+    size_t cnt = ((size_t)b->proto.T * (size_t)n_slots * 4 + 255) & ~(size_t)255;
+    size_t part = (size_t)b->proto.num_sms * 2 * TILE_ROWS * 4 * sizeof(double);
+    return cnt + part;
+}
+
+cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const uint8_t* xq, int64_t x_rows, int64_t x_slot_div,
+                                  void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st) {
+    b200q_weight v = b->proto;  // virtual weight: the selected experts' tiles back to back
+    v.T = b->proto.T * n_slots;
+    MatvecPlan plan;
+    cudaError_t e = matvec_plan(&v, 1, &plan, 0);
+    if (e != cudaSuccess) return e;
+    if (plan.stage_bytes - (v.chunk_bytes + ACT_REC_BYTES) < 16) return cudaErrorInvalidValue;  // room for the per-stage skip flag
+    MatvecParams p = {};
+    p.w = nullptr;
+    p.xq = xq;
+    p.y = y;
+    p.bias = nullptr;
+    size_t cnt = ((size_t)v.T * 4 + 255) & ~(size_t)255;
+    p.ws_cnt = reinterpret_cast<unsigned int*>(ws);
+    p.ws_part = reinterpret_cast<double*>(ws + cnt);
+    p.N = b->proto.N;
+    p.M = 1;
+    p.y_dtype = y_dtype;
+    p.ldy = b->proto.N;
+    p.KC = v.KC;
+    p.C = v.T * v.KC;
+    p.gpc = v.gpc;
+    p.nstages = plan.nstages;
+    p.chunk_bytes = v.chunk_bytes;
+    p.stage_bytes = plan.stage_bytes;
+    p.w_table = b->table_dev;
+    p.sel = sel_dev;
+    p.tpw = (int)b->proto.T;
+    p.x_rows = (int)x_rows;
+    p.x_slot_div = (int)x_slot_div;
+    p.y_slot_stride = y_slot_stride;
+    return launch_family(v.family, p, 1, plan.grid, plan.smem_bytes, st);
 }
 
 }  // namespace b200q

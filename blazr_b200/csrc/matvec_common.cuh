@@ -38,6 +38,15 @@ struct MatvecParams {
     const float* norm_w;
     float eps;
     const float* gate_up;
+    // grouped (expert bank) mode, w_table != null: the launch runs n_slots independent M = 1 matvecs; slot s uses the
+    // weight w_table[sel[s]], the activation record row s / x_slot_div of xq (x_rows rows per k-chunk) and writes
+    // y[s * y_slot_stride + n].  Tiles are numbered slot-major (tile t -> slot t / tpw), so the stream-K split, the
+    // partial slots and the fix-up work unchanged on the concatenated chunk range.
+    const uint8_t* const* w_table;
+    const int32_t* sel;
+    int tpw;              // tiles per weight
+    int x_rows, x_slot_div;
+    int64_t y_slot_stride;
 };
 
 __device__ __forceinline__ int64_t sk_begin(int64_t g, int64_t C, int64_t G) { return g * C / G; }

@@ -167,26 +167,50 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             const uint64_t pol = policy_evict_first();
             const uint32_t xbytes = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
             const uint32_t wbytes = (uint32_t)p.chunk_bytes;
-            // j-th processed chunk -> (weight address, k-chunk index)
-            const uint8_t* base = p.w + c0 * (int64_t)wbytes;
-            auto chunk_src = [&](int j) -> const uint8_t* {
-                if (j < sp.nH) return base + (size_t)j * wbytes;
-                if (j < sp.nH + sp.nT) return base + (size_t)(sp.nH + sp.nF + (j - sp.nH)) * wbytes;
-                return base + (size_t)(sp.nH + (j - sp.nH - sp.nT)) * wbytes;
+            const bool grouped = p.w_table != nullptr;
+            const int64_t cpw = (int64_t)p.tpw * p.KC;  // grouped: chunks per weight
+            if (grouped) pdl_wait();                      // the expert selection is produced by the preceding kernel
+            // j-th processed chunk -> (weight address, activation record address)
+            auto chunk_vc = [&](int j) -> int64_t {      // chunk index in the (concatenated) chunk array
+                if (j < sp.nH) return c0 + j;
+                if (j < sp.nH + sp.nT) return c0 + sp.nH + sp.nF + (j - sp.nH);
+                return c0 + sp.nH + (j - sp.nH - sp.nT);
             };
-            auto chunk_kc = [&](int j) -> int {
-                if (j < sp.nH) return sp.kcH + j;
-                if (j < sp.nH + sp.nT) return j - sp.nH;
-                return (j - sp.nH - sp.nT) % KC;
+            auto chunk_src = [&](int j) -> const uint8_t* {
+                const int64_t vc = chunk_vc(j);
+                if (!grouped) return p.w + vc * (int64_t)wbytes;
+                const int64_t slot = vc / cpw;
+                const int e = p.sel[slot];
+                return e < 0 ? nullptr : p.w_table[e] + (vc - slot * cpw) * (int64_t)wbytes;
+            };
+            auto chunk_x = [&](int j) -> const uint8_t* {
+                int kc;
+                if (j < sp.nH) kc = sp.kcH + j;
+                else if (j < sp.nH + sp.nT) kc = j - sp.nH;
+                else kc = (j - sp.nH - sp.nT) % KC;
+                if (!grouped) return p.xq + (size_t)kc * xbytes;
+                const int64_t slot = chunk_vc(j) / cpw;
+                return p.xq + ((size_t)kc * p.x_rows + (size_t)(slot / p.x_slot_div)) * ACT_REC_BYTES;
             };
             // Phase 1 (before griddepcontrol.wait): weights do not depend on the preceding kernels.  Fill the
             // shared-memory ring and ask the TMA engine to pull the rest of this CTA's range into L2, so HBM
             // keeps streaming across the kernel boundary while the predecessor drains.
             const int pre = n_chunks < nst ? n_chunks : nst;
-            for (int j = 0; j < pre; j++) {
-                mbar_arrive_expect_tx(&full[j], wbytes + xbytes);
-                bulk_g2s_hint(stages + (size_t)j * p.stage_bytes, chunk_src(j), wbytes, &full[j], pol);
-            }
+            // grouped mode: a slot whose selection is negative (expert not hosted by this rank) is skipped -- no weight
+            // copy, a flag behind the stage's activation record tells the consumers to leave the accumulators at zero
+            auto issue_w = [&](int j, uint8_t* st, uint64_t* bar) {
+                const uint8_t* src = chunk_src(j);
+                if (grouped) {
+                    const bool skip = src == nullptr;
+                    *reinterpret_cast<volatile int*>(st + wbytes + xbytes) = skip ? 1 : 0;
+                    mbar_arrive_expect_tx(bar, (skip ? 0u : wbytes) + xbytes);
+                    if (skip) return;
+                } else {
+                    mbar_arrive_expect_tx(bar, wbytes + xbytes);
+                }
+                bulk_g2s_hint(st, src, wbytes, bar, pol);
+            };
+            for (int j = 0; j < pre; j++) issue_w(j, stages + (size_t)j * p.stage_bytes, &full[j]);
             int npf = n_chunks - pre;
             if (npf > p.l2_prefetch_chunks) npf = p.l2_prefetch_chunks;
             for (int j = pre; j < pre + npf; j++)
@@ -195,15 +219,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             if (p.trace) p.trace[g * 8 + 4] = globaltimer_ns();
             if (!PRO)
                 for (int j = 0; j < pre; j++)
-                    bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[j]);
+                    bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, chunk_x(j), xbytes, &full[j]);
             int s = 0;
             uint32_t ph = 0;  // second use of each stage waits for the consumers' first release (phase 0)
             for (int j = pre; j < n_chunks; j++) {
                 mbar_wait(&empty[s], ph);
                 uint8_t* st = stages + (size_t)s * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[s], wbytes + xbytes);
-                bulk_g2s_hint(st, chunk_src(j), wbytes, &full[s], pol);
-                if (!PRO) bulk_g2s(st + wbytes, p.xq + (size_t)chunk_kc(j) * xbytes, xbytes, &full[s]);
+                issue_w(j, st, &full[s]);
+                if (!PRO) bulk_g2s(st + wbytes, chunk_x(j), xbytes, &full[s]);
                 if (++s == nst) { s = 0; ph ^= 1u; }
             }
         }
@@ -239,6 +262,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
             // last arriver: sum the partials in CTA order (deterministic).  Every load of a batch of NB contributors
             // x all passes is issued before the first add, so the reduction costs one L2 round trip per NB contributors.
+            const int64_t tql = p.w_table ? tq % p.tpw : tq;                      // tile index inside its weight
+            const int64_t ybase = p.w_table ? (tq / p.tpw) * p.y_slot_stride : 0;  // grouped: output of slot tq / tpw
             constexpr int PASSES = 2 * MB;                       // 64 doubles (one double2 per lane) per pass
             constexpr int NB = MB == 1 ? 8 : (MB == 2 ? 4 : 2);  // contributors in flight
             double2 sum[PASSES];
@@ -266,8 +291,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
-                    const int64_t n = tq * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, (float)(sv[e] + (p.bias ? (double)p.bias[n] : 0.0)));
+                    const int64_t n = tql * TILE_ROWS + rr;
+                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, (float)(sv[e] + (p.bias ? (double)p.bias[n] : 0.0)));
                 }
             }
             if (lane == 0) p.ws_cnt[tq] = 0u;
@@ -318,7 +343,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             bsA[m] = (int)(int16_t)(bs & 0xFFFFu);
             bsB[m] = (int)(int16_t)(bs >> 16);
         }
-        if (!(p.debug_flags & 1))
+        const bool skip_chunk = p.w_table != nullptr && *reinterpret_cast<const volatile int*>(wc + p.chunk_bytes + p.M * ACT_REC_BYTES) != 0;
+        if (!(p.debug_flags & 1) && !skip_chunk)
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++) {
             const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
@@ -372,13 +398,15 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         if (seg == 2) {
             if (i == 0) {
 #pragma unroll
+                const int64_t tl = p.w_table ? t % p.tpw : t;
+                const int64_t ybase = p.w_table ? (int64_t)(t / p.tpw) * p.y_slot_stride : 0;
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
-                    const int64_t n = (int64_t)t * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
+                    const int64_t n = tl * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
                     if (n < p.N) {
                         const double bv = p.bias ? (double)p.bias[n] : 0.0;
 #pragma unroll
                         for (int m = 0; m < MB; m++)
-                            if (m < p.M) store_out(p.y, p.y_dtype, (int64_t)m * p.ldy + n, (float)(acc[s4][m] + bv));
+                            if (m < p.M) store_out(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, (float)(acc[s4][m] + bv));
                     }
                 }
             }

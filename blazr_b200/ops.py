@@ -55,6 +55,7 @@ EXPORTS = [
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
     "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
+    "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
 ]
 
 _lib = None
@@ -73,6 +74,9 @@ def lib() -> C.CDLL:
         L.b200q_launch_count.restype = C.c_int64
         L.b200q_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
         L.b200q_act_bytes.argtypes = [C.c_int64, C.c_int64]
+        L.b200q_bank_workspace_bytes.restype = C.c_size_t
+        L.b200q_bank_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
+        L.b200q_bank_get.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -279,6 +283,109 @@ class B200Client:
         _check(lib().b200q_int_partials(w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(M), C.c_void_p(out.data_ptr()),
                                         _stream_ptr(xq.device)))
         return out
+
+
+class ExpertBank:
+    """E weights of one format and shape behind a device pointer table (one projection of a stacked expert tensor).
+    Members stay owned by their QuantWeight wrappers, which the bank keeps alive."""
+
+    def __init__(self, experts):
+        self.experts = list(experts)
+        arr = (C.c_void_p * len(self.experts))(*[w.handle for w in self.experts])
+        h = C.c_void_p()
+        _check(lib().b200q_bank_create(arr, C.c_int32(len(self.experts)), C.byref(h)))
+        self._h = h
+        self.device = self.experts[0].device
+        self.N, self.K, self.K_pad = self.experts[0].N, self.experts[0].K, self.experts[0].K_pad
+        self._ws = {}
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __len__(self):
+        return len(self.experts)
+
+    def set(self, e: int, w: QuantWeight):
+        _check(lib().b200q_bank_set(self._h, C.c_int32(e), w.handle, _stream_ptr(self.device)))
+        self.experts[e] = w
+
+    def workspace(self, n_slots: int) -> torch.Tensor:
+        ws = self._ws.get(n_slots)
+        if ws is None:
+            ws = torch.zeros(max(256, int(lib().b200q_bank_workspace_bytes(self._h, C.c_int64(n_slots)))), dtype=torch.uint8, device=self.device)
+            self._ws[n_slots] = ws
+        return ws
+
+    def matmul_q8(self, sel: torch.Tensor, xq: torch.Tensor, x_rows: int, x_slot_div: int, out: Optional[torch.Tensor] = None,
+                  workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """y[s, :] = W[sel[s]] . x[s // x_slot_div]   (sel: device int32 [n_slots]; xq: quantised records of x_rows rows)"""
+        assert sel.is_cuda and sel.dtype == torch.int32
+        n = sel.numel()
+        if out is None:
+            out = torch.empty((n, self.N), dtype=torch.float32, device=self.device)
+        ws = workspace if workspace is not None else self.workspace(n)
+        _check(lib().b200q_moe_matmul_q8(self._h, C.c_void_p(sel.data_ptr()), C.c_int64(n), C.c_void_p(xq.data_ptr()), C.c_int64(x_rows),
+                                         C.c_int64(x_slot_div), C.c_void_p(out.data_ptr()), C.c_int32(_TORCH2DT[out.dtype]),
+                                         C.c_int64(out.stride(0)), C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()),
+                                         _stream_ptr(self.device)))
+        return out
+
+    def free(self):
+        if self._h is not None:
+            lib().b200q_bank_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class ExpertWeights:
+    """mirror of boostr::ExpertWeights (reference src/engine/executor_cache.rs:19,344-348): one expert's projections.
+    gate_up is the row-fused [2 * ffn, hidden] weight (gate rows first) the decode path launches once."""
+    gate_up: QuantWeight
+    down_proj: QuantWeight
+
+
+class MoeMlp:
+    """Decode-time mixture-of-experts MLP over two expert banks (gate|up fused, down), the operator behind
+    get_expert_weights / set_expert_weights (reference executor_cache.rs:260,283).  `local` lists the expert ids this
+    rank hosts (expert parallelism, SURVEY 8e: each rank runs its local selected experts on the replicated hidden state;
+    blazr_b200/tp.py:ep_local_slots masks the non-local slots and the caller all-reduces the partial outputs)."""
+
+    def __init__(self, client: "B200Client", experts, ffn: int, hidden: int, local=None):
+        self.client = client
+        self.E = len(experts)
+        self.ffn, self.hidden = ffn, hidden
+        self.local = list(range(self.E)) if local is None else list(local)
+        self._experts = list(experts)
+        self.gu = ExpertBank([e.gate_up for e in experts])
+        self.down = ExpertBank([e.down_proj for e in experts])
+
+    def get_expert_weights(self, e: int) -> ExpertWeights:
+        return self._experts[e]
+
+    def set_expert_weights(self, e: int, w: ExpertWeights):
+        self.gu.set(e, w.gate_up)
+        self.down.set(e, w.down_proj)
+        self._experts[e] = w
+
+    def forward_decode(self, x: torch.Tensor, sel: torch.Tensor, gate_w: torch.Tensor) -> torch.Tensor:
+        """x [T, hidden] f32, sel [T, top_k] int32 (bank-local expert indices), gate_w [T, top_k] f32 -> [T, hidden].
+        Three launches: grouped gate|up matvec, SwiGLU + quantise, grouped down matvec; the weighted combine is torch."""
+        T, top_k = sel.shape
+        n = T * top_k
+        xq = self.client.quantize_act(x)
+        gu = self.gu.matmul_q8(sel.reshape(-1), xq, T, top_k)                      # [n, 2 ffn]
+        aq = torch.empty(int(lib().b200q_act_bytes(C.c_int64(self.ffn), C.c_int64(n))), dtype=torch.uint8, device=x.device)
+        _check(lib().b200q_swiglu_quant(C.c_void_p(gu.data_ptr()), C.c_int64(self.ffn), C.c_int64(n), C.c_void_p(aq.data_ptr()),
+                                        _stream_ptr(x.device)))
+        y = self.down.matmul_q8(sel.reshape(-1), aq, n, 1)                           # [n, hidden]
+        return (y.reshape(T, top_k, self.hidden) * gate_w.unsqueeze(-1)).sum(dim=1)
 
 
 def launch_count() -> int:

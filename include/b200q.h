@@ -139,6 +139,25 @@ int32_t b200q_quantize_act(const void* x, int32_t x_dtype, int64_t M, int64_t K,
                            void* xq, void* stream);
 int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* y, int32_t y_dtype, int64_t ldy,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* ---- expert banks (MoE): reference boostr::ExpertWeights{gate_proj, up_proj, down_proj}, stacked
+ * [num_experts, dim_in, dim_out] and sliced per expert (src/engine/executor_cache.rs:19,218-228,260,283,344-348).
+ * A bank is a device-resident table of E weights of one format and shape; b200q_bank_set is the
+ * set_expert_weights analogue (placement changes swap one table entry, members are not owned).
+ * b200q_moe_matmul_q8 runs n_slots independent M = 1 matvecs in ONE stream-K launch: slot s uses expert
+ * sel[s] (device int32, produced by the router just ahead in the stream), the quantised activation row
+ * s / x_slot_div of xq (an activation buffer of x_rows rows, b200q_act_bytes(K, x_rows) layout) and writes
+ * y[s * y_slot_stride + n].  x_slot_div = top_k shares one token's activation among its experts (gate/up);
+ * x_slot_div = 1 gives every slot its own row (down).  Same arithmetic, bit for bit, as b200q_matmul_q8 per slot. */
+typedef struct b200q_bank b200q_bank;
+int32_t b200q_bank_create(const b200q_weight* const* experts, int32_t E, b200q_bank** out);
+int32_t b200q_bank_free(b200q_bank* b);
+int32_t b200q_bank_set(b200q_bank* b, int32_t e, const b200q_weight* w, void* stream);
+const b200q_weight* b200q_bank_get(const b200q_bank* b, int32_t e);
+size_t b200q_bank_workspace_bytes(const b200q_bank* b, int64_t n_slots);
+int32_t b200q_moe_matmul_q8(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const void* xq, int64_t x_rows,
+                            int64_t x_slot_div, void* y, int32_t y_dtype, int64_t y_slot_stride, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* Decode matmuls with a fused activation producer (M <= 4): the consumer warps build the quantised activation in
  * shared memory while the first weight chunks are in flight, so no separate norm / SwiGLU kernel runs.
  *   norm  : h = h_in (+ delta, nullable); h_out (nullable; written once) = h; x = quant(rmsnorm(h) * norm_w); y = x . W^T
