@@ -99,15 +99,19 @@ __global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float*
 }
 
 // ------------------------------------------------------------------------------------------------
-// act = silu(gate) * up ; xq = quant(act)       gate_up: [M, 2*F] (gate first), F % 256 == 0
+// act = silu(gate) * up ; xq = quant(act)       gate_up: [M, 2*F] (gate first), F % 32 == 0; the records are
+// zero-padded up to the next multiple of 256 (DeepSeek-V2-Lite experts: F = 1408 = 5.5 chunks)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restrict__ gu, int F, int M, uint8_t* __restrict__ xq) {
     pdl_launch_dependents();
     pdl_wait();
     const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
     const int k = kc * CHUNK_K + t;
-    const float g = gu[(size_t)m * 2 * F + k], u = gu[(size_t)m * 2 * F + F + k];
-    const float v = __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, det_expf(-g))), u);
+    float v = 0.0f;
+    if (k < F) {
+        const float g = gu[(size_t)m * 2 * F + k], u = gu[(size_t)m * 2 * F + F + k];
+        v = __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, det_expf(-g))), u);
+    }
     quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
 }
 
@@ -345,8 +349,8 @@ int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_
 }
 
 int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream) {
-    if (!gate_up || !xq || F <= 0 || F % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
-    cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)(F / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
+    if (!gate_up || !xq || F <= 0 || F % 32 || M <= 0 || M > 65535) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)((F + CHUNK_K - 1) / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
                                (int)M, (uint8_t*)xq);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }

@@ -49,3 +49,19 @@ def plan(hidden: int, n_heads: int, n_kv_heads: int, head_dim: int, ffn: int, vo
     v0, v1 = ops.shard_range(vocab, rank, world, granule=128)
     return TpPlan(rank, world, h1 - h0, k1 - k0, (h0 * head_dim, h1 * head_dim), (k0 * head_dim, k1 * head_dim),
                   (h0 * head_dim, h1 * head_dim), (f0, f1), (f0, f1), (v0, v1))
+
+
+# ------------------------------------------------------------------------------------------------
+# expert parallelism: experts are partitioned num_experts / world per rank with the same
+# shard_range rule; for decode every rank runs its local selected experts on the replicated hidden state and the
+# partial outputs are all-reduced (single exchange).
+# ------------------------------------------------------------------------------------------------
+def expert_range(num_experts: int, rank: int, world: int) -> Tuple[int, int]:
+    return ops.shard_range(num_experts, rank, world)
+
+
+def ep_local_slots(sel, gate_w, e0: int, e1: int):
+    """sel [T, top_k] global expert ids (int32 tensor), gate_w [T, top_k] -> (bank-local ids with -1 for experts
+    hosted elsewhere, gate weights with those slots zeroed).  Pure tensor ops: graph-capturable, no host sync."""
+    local = (sel >= e0) & (sel < e1)
+    return (sel - e0).masked_fill(~local, -1), gate_w * local.to(gate_w.dtype)

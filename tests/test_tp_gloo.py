@@ -85,3 +85,52 @@ def test_tp_validation_matches_reference_rule():
     assert pl.q_rows == (3072, 4096) and pl.kv_rows == (384, 512)
     assert pl.down_cols == (10752, 14336) and (pl.down_cols[1] - pl.down_cols[0]) // 256 == 14
     assert pl.o_cols[1] - pl.o_cols[0] == 1024
+
+
+def _ep_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # expert parallelism: 8 experts over 2 ranks, top-3 routing of 2 tokens; every rank
+        # evaluates its local selected experts with the oracle on the replicated hidden state, all-reduce combines
+        E, top_k, hidden, ffn = 8, 3, 256, 128
+        t = synth.GGML["Q8_0"]
+        gate = [synth.random_ggml(t, ffn, hidden, seed=40 + e) for e in range(E)]
+        down = [synth.random_ggml(t, hidden, ffn, seed=60 + e) for e in range(E)]
+        x = synth.random_act(2, hidden, seed=8)
+        sel = torch.tensor([[1, 6, 3], [0, 6, 7]], dtype=torch.int32)
+        gw = torch.tensor([[0.5, 0.3, 0.2], [0.6, 0.25, 0.15]], dtype=torch.float32)
+
+        def expert(e, xr):
+            g = oracle.matmul_ggml_f32(t, gate[e], ffn, hidden, xr)
+            return oracle.matmul_ggml_f32(t, down[e], hidden, ffn, np.maximum(g, 0))
+
+        full = np.zeros((2, hidden), dtype=np.float32)
+        for tk in range(2):
+            for j in range(top_k):
+                full[tk] += float(gw[tk, j]) * expert(int(sel[tk, j]), x[tk:tk + 1])[0]
+        e0, e1 = tp.expert_range(E, rank, world)
+        ls, lg = tp.ep_local_slots(sel, gw, e0, e1)
+        part = np.zeros((2, hidden), dtype=np.float32)
+        for tk in range(2):
+            for j in range(top_k):
+                if int(ls[tk, j]) >= 0:
+                    part[tk] += float(lg[tk, j]) * expert(e0 + int(ls[tk, j]), x[tk:tk + 1])[0]
+                else:
+                    assert float(lg[tk, j]) == 0.0
+        pt = torch.from_numpy(part)
+        dist.all_reduce(pt)
+        ret[rank] = ((e0, e1), float(np.abs(pt.numpy() - full).max() / np.abs(full).max()), int((ls >= 0).sum()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ep2_local_experts_all_reduce_over_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ep_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0][0] == (0, 4) and ret[1][0] == (4, 8)
+    assert ret[0][1] < 1e-6 and ret[1][1] < 1e-6
+    assert ret[0][2] + ret[1][2] == 6  # every routed slot is hosted by exactly one rank
