@@ -85,6 +85,14 @@ __device__ __forceinline__ float det_expf(float x) {
     return __fmul_rn(p, __int_as_float(((int)n + 127) << 23));
 }
 
+// one elected lane of a converged warp (the compiler then emits tcgen05 / TMA instructions of the guarded region
+// without per-instruction uniformity loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- programmatic dependent launch ----
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -40,7 +40,7 @@ struct GemmParams {
     int y_dtype;
     int T, KC, MT, Mt;
     int gpc, chunk_bytes, nw, w_stage_bytes, x_stage_bytes;
-    int nslots, a_col, nx;
+    int nslots, a_col, nx, xsub;   // xsub: 64-k sub-tiles per X stage (1 or 4)
     int dq_warps;      // 8 (wide M tiles) or 16 + dedicated epilogue warps + two accumulators (Mt <= 128)
     int splits;        // split-K factor (serial K loop is the latency floor when there are fewer tiles than SMs)
     float* partial;    // [splits][M][N] f32 when splits > 1
@@ -187,8 +187,10 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int sp_ = tile % p.splits, mt = (tile / p.splits) % p.MT;
                 const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
-                const uint8_t* src = p.xs + ((size_t)mt * KS + 4 * kc0) * p.x_stage_bytes;
-                for (int ks = 4 * kc0; ks < 4 * kc1; ks++) {
+                // one X stage = xsub consecutive 64-k sub-tiles (contiguous in the staged layout): 1 for wide M tiles,
+                // 4 (a whole chunk) for skinny ones, where per-stage handshakes would otherwise pace the MMA issuer
+                const uint8_t* src = p.xs + ((size_t)mt * KS + 4 * kc0) * (size_t)(p.Mt * 128);
+                for (int ks = 4 * kc0; ks < 4 * kc1; ks += p.xsub) {
                     mbar_wait(&empty_x[s], ph);
                     mbar_arrive_expect_tx(&full_x[s], (uint32_t)p.x_stage_bytes);
                     bulk_g2s(xst + (size_t)s * p.x_stage_bytes, src, (uint32_t)p.x_stage_bytes, &full_x[s]);
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         }
     } else if (warp == 1) {
         // ===================== single-thread MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int xs = 0, as = 0, acc = 0;
             uint32_t xph = 0, aph = 0, eph0 = 1, eph1 = 1;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -214,16 +216,30 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
                 for (int kc = kc0; kc < kc1; kc++) {
                     mbar_wait(&a_full[as], aph);  // a whole dequantised chunk (4 x 64 k) is in TMEM
                     const uint32_t a_chunk = tmem + p.a_col + as * 128;
-#pragma unroll 1
-                    for (int j = 0; j < 4; j++) {
+                    if (p.xsub == 4) {
                         mbar_wait(&full_x[xs], xph);
                         tc_fence_after();
-                        const uint64_t bdesc = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
+                        const uint64_t bdesc0 = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
+                        const uint64_t sub = (uint64_t)((p.Mt * 128) >> 4);  // descriptor address units of 16 B
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++)
-                            tc_mma_ts(tmem + d_col, a_chunk + j * 32 + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
+                        for (int j = 0; j < 4; j++)
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++)
+                                tc_mma_ts(tmem + d_col, a_chunk + j * 32 + kk * 8, bdesc0 + j * sub + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
                         tc_commit(&empty_x[xs]);
                         if (++xs == p.nx) { xs = 0; xph ^= 1u; }
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 4; j++) {
+                            mbar_wait(&full_x[xs], xph);
+                            tc_fence_after();
+                            const uint64_t bdesc = make_b_desc(smem_u32(xst + (size_t)xs * p.x_stage_bytes));
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++)
+                                tc_mma_ts(tmem + d_col, a_chunk + j * 32 + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
+                            tc_commit(&empty_x[xs]);
+                            if (++xs == p.nx) { xs = 0; xph ^= 1u; }
+                        }
                     }
                     tc_commit(&a_empty[as]);
                     if (++as == p.nslots) { as = 0; aph ^= 1u; }

@@ -54,7 +54,9 @@ static int pick_splits(const b200q_weight* w, int MT, int64_t M) {
         const int64_t items = tiles * s;
         const int64_t waves = (items + sms - 1) / sms;
         double eff = (double)items / (double)(waves * sms);
-        eff -= 0.01 * (s - 1);  // partial-sum traffic and a shorter K loop per item
+        // partial sums cost s x M x N f32 written and read again, relative to the packed weight bytes streamed once
+        const double extra = s > 1 ? (double)s * (double)M * (double)w->N * 8.0 / (double)w->device_bytes : 0.0;
+        eff = eff / (1.0 + extra) - 0.01 * (s - 1);
         if (eff > best_eff) { best_eff = eff; best = s; }
     }
     return best;
@@ -120,11 +122,13 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     p.gpc = w->gpc;
     p.chunk_bytes = w->chunk_bytes;
     p.w_stage_bytes = (w->chunk_bytes + 127) & ~127;
-    p.x_stage_bytes = Mt * 128;
+    p.xsub = Mt <= 64 ? 4 : 1;
+    p.x_stage_bytes = Mt * 128 * p.xsub;
     // activation ring: deep enough to cover the L2 latency when the MMAs are short (small Mt), <= 128 KB
     int nx = (128 * 1024) / p.x_stage_bytes;
     if (nx > GT_NX) nx = GT_NX;
     if (nx < 4) nx = 4;
+    if (p.xsub == 4) nx = Mt <= 32 ? 4 : 3;  // whole-chunk stages: keep the shared memory for the weight ring (the HBM stream)
     p.nx = nx;
     int avail = 227 * 1024 - GT_HDR - nx * p.x_stage_bytes;
     int nw = avail / p.w_stage_bytes;
