@@ -257,7 +257,16 @@ def run_b200(args):
     achieved = bytes_gu / (us_gu * 1e-6) / 1e9
     # whole-step view: all matvec weight bytes over the step time
     step_bytes = dec.weight_bytes
-    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/, tools/ncu_summary.py)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tk = tj.get(f"{decode.layer_formats(cfg, scheme, 0)['gate']}:{w0.N}x{w0.K}:M{M}")
+        if tk:
+            traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
+    except Exception:
+        traffic = None
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
             "kernel": f"matvec_kernel<{decode.layer_formats(cfg, scheme, 0)['gate']},{M}> gate|up N={w0.N} K={w0.K}", "us_per_launch": us_gu,
             "algorithmic_bytes_per_launch": bytes_gu, "peak_kind": pk_kind + " burst (kernel timed alone)",
             "step_weight_bytes": step_bytes, "step_GBs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
