@@ -347,7 +347,7 @@ int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* 
                         size_t workspace_bytes, void* stream) {
     if (!w || !xq || !y || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
     if (M < 1 || M > 4) return fail(B200Q_ERR_UNSUPPORTED, "matmul_q8 handles M in [1,4] (got %lld); use b200q_matmul", (long long)M);
-    if (ldy < w->N || y_dtype < 0 || y_dtype > 2) return fail(B200Q_ERR_INVALID_ARG, "bad ldy / y_dtype");
+    if (ldy < w->N || y_dtype < 0 || y_dtype > 3) return fail(B200Q_ERR_INVALID_ARG, "bad ldy / y_dtype");  // 3 = f64 partial sums (TP)
     if (workspace_bytes < align256(matvec_ws_bytes(w, M))) return fail(B200Q_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, align256(matvec_ws_bytes(w, M)));
     CUDA_TRY(launch_matvec(w, (const uint8_t*)xq, M, y, y_dtype, ldy, (uint8_t*)workspace, (cudaStream_t)stream));
     return B200Q_OK;

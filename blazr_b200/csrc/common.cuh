@@ -136,6 +136,11 @@ __device__ __forceinline__ void store_out(void* y, int dtype, int64_t idx, float
     else if (dtype == 1) reinterpret_cast<__half*>(y)[idx] = __float2half_rn(v);
     else reinterpret_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
 }
+// matvec epilogue: the exact f64 sum is rounded once to the output type, or kept (dtype 3) for the TP all-reduce
+__device__ __forceinline__ void store_out_d(void* y, int dtype, int64_t idx, double v) {
+    if (dtype == 3) reinterpret_cast<double*>(y)[idx] = v;
+    else store_out(y, dtype, idx, (float)v);
+}
 __device__ __forceinline__ float load_in(const void* x, int dtype, int64_t idx) {
     if (dtype == 0) return reinterpret_cast<const float*>(x)[idx];
     if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(x)[idx]);

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
                     const int64_t n = tql * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) store_out(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, (float)(sv[e] + (p.bias ? (double)p.bias[n] : 0.0)));
+                    if (n < p.N && m < p.M) store_out_d(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, sv[e] + (p.bias ? (double)p.bias[n] : 0.0));
                 }
             }
             if (lane == 0) p.ws_cnt[tq] = 0u;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                         const double bv = p.bias ? (double)p.bias[n] : 0.0;
 #pragma unroll
                         for (int m = 0; m < MB; m++)
-                            if (m < p.M) store_out(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, (float)(acc[s4][m] + bv));
+                            if (m < p.M) store_out_d(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, acc[s4][m] + bv);
                     }
                 }
             }

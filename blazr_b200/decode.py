@@ -231,6 +231,12 @@ class Decoder:
         self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0"  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
+        # tensor parallel: one-shot NVLink all-reduce of the f64 partial sums (csrc/comm.cu); B200Q_TP_NCCL=1 falls back
+        # to torch.distributed (NCCL) all-reduce of f32 partials for comparison
+        self.comm = None
+        if tp_world > 1 and _os.environ.get("B200Q_TP_NCCL", "0") == "0":
+            self.comm = ops.PeerComm(tp_rank, tp_world, M * H, dev, group)
+            self.part64 = torch.zeros((M, H), dtype=torch.float64, device=dev)
 
     # ---- weights ------------------------------------------------------------------------------------
     def _fused(self, layer: int, parts, K: int, host: Optional[HostModel], kslice=None) -> List[_Linear]:
@@ -305,10 +311,23 @@ class Decoder:
     def _matvec(self, lins: List[_Linear], xq: torch.Tensor, out: torch.Tensor):
         L = ops.lib()
         st = ops._stream_ptr(self.dev)
+        dt = ops.F64 if out.dtype == torch.float64 else ops.F32
         for ln in lins:
             ops._check(L.b200q_matmul_q8(ln.w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(self.M),
-                                         C.c_void_p(out.data_ptr() + 4 * ln.col0), C.c_int32(ops.F32), C.c_int64(out.stride(0)),
+                                         C.c_void_p(out.data_ptr() + out.element_size() * ln.col0), C.c_int32(dt), C.c_int64(out.stride(0)),
                                          C.c_void_p(ln.ws.data_ptr()), C.c_size_t(ln.ws.numel()), st))
+
+    def _rowpar(self, lins: List[_Linear], xq: torch.Tensor, out: torch.Tensor):
+        """row-parallel projection + all-reduce(sum) into out (f32).  TP: the matvec leaves its exact f64 partial sums,
+        the one-shot NVLink all-reduce sums them in rank order and rounds once (bit-identical to the 1-GPU output)."""
+        if self.world == 1:
+            self._matvec(lins, xq, out)
+        elif self.comm is not None:
+            self._matvec(lins, xq, self.part64)
+            self.comm.allreduce_f64(self.part64, out)
+        else:
+            self._matvec(lins, xq, out)
+            torch.distributed.all_reduce(out, group=self.group)
 
     def _allreduce(self, t: torch.Tensor):
         if self.world > 1:
@@ -348,8 +367,7 @@ class Decoder:
             ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
                                            C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
                                            P(self.xq_attn), None, st))
-            self._matvec(lay["o"], self.xq_attn, self.delta)
-            self._allreduce(self.delta)
+            self._rowpar(lay["o"], self.xq_attn, self.delta)
             delta = self.delta
             if fused:
                 matvec_norm(lay["gu"], lay["mlp_norm"], self.gu)
@@ -365,8 +383,7 @@ class Decoder:
                 delta = self.delta2
             else:
                 ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
-                self._matvec(lay["down"], self.xq_ff, self.delta2)
-                self._allreduce(self.delta2)
+                self._rowpar(lay["down"], self.xq_ff, self.delta2)
                 delta = self.delta2
         if fused:
             matvec_norm(self.head, self.final_norm, self.logits_local)
@@ -388,6 +405,8 @@ class Decoder:
         n = 1 + glue + len(self.head) + 1  # embed, (final norm), head, argmax
         for lay in self.layers:
             n += 2 * glue + len(lay["qkv"]) + 1 + len(lay["o"]) + len(lay["gu"]) + sw + len(lay["down"])
+            if self.comm is not None:
+                n += 2  # the two one-shot all-reduce kernels (ours; NCCL kernels are not counted)
         return n
 
     def capture(self):

@@ -27,8 +27,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200q.so")
 
-F32, F16, BF16 = 0, 1, 2
-_TORCH2DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+F32, F16, BF16, F64 = 0, 1, 2, 3
+_TORCH2DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float64: F64}
 PATH_AUTO, PATH_MATVEC, PATH_GEMM = 0, 1, 2
 
 
@@ -55,6 +55,7 @@ EXPORTS = [
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
     "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
+    "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free",
     "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
 ]
 
@@ -386,6 +387,39 @@ class MoeMlp:
                                         _stream_ptr(x.device)))
         y = self.down.matmul_q8(sel.reshape(-1), aq, n, 1)                           # [n, hidden]
         return (y.reshape(T, top_k, self.hidden) * gate_w.unsqueeze(-1)).sum(dim=1)
+
+
+class PeerComm:
+    """One-shot NVLink all-reduce context (include/b200q.h b200q_comm_*).  `group` is only used once, to all-gather
+    the CUDA IPC handles; the data path never touches NCCL."""
+
+    def __init__(self, rank: int, world: int, max_elems: int, device: torch.device, group=None):
+        self.rank, self.world, self.device = rank, world, device
+        h = C.c_void_p()
+        _check(lib().b200q_comm_create(C.c_int32(rank), C.c_int32(world), C.c_int64(max_elems), C.c_int32(device.index or 0), C.byref(h)))
+        self._h = h
+        mine = (C.c_uint8 * 64)()
+        _check(lib().b200q_comm_handle(self._h, mine))
+        handles = [bytes(mine)]
+        if world > 1:
+            import torch.distributed as dist
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(mine), group=group)
+        buf = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        _check(lib().b200q_comm_connect(self._h, buf))
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
+
+    def allreduce_f64(self, src: torch.Tensor, dst: torch.Tensor):
+        assert src.dtype == torch.float64 and dst.dtype == torch.float32 and src.numel() == dst.numel()
+        _check(lib().b200q_allreduce_f64(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int64(src.numel()),
+                                         _stream_ptr(self.device)))
+
+    def free(self):
+        if self._h is not None:
+            lib().b200q_comm_free(self._h)
+            self._h = None
 
 
 def launch_count() -> int:

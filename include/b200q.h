@@ -57,7 +57,7 @@ typedef enum b200q_status {
     B200Q_ERR_NO_DEVICE = -5
 } b200q_status;
 
-typedef enum b200q_dtype { B200Q_F32 = 0, B200Q_F16 = 1, B200Q_BF16 = 2 } b200q_dtype;
+typedef enum b200q_dtype { B200Q_F32 = 0, B200Q_F16 = 1, B200Q_BF16 = 2, B200Q_F64 = 3 /* b200q_matmul_q8 output only: un-rounded partial sums */ } b200q_dtype;
 
 /* internal format families, reported by b200q_weight_info */
 typedef enum b200q_family {
@@ -157,6 +157,18 @@ size_t b200q_bank_workspace_bytes(const b200q_bank* b, int64_t n_slots);
 int32_t b200q_moe_matmul_q8(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const void* xq, int64_t x_rows,
                             int64_t x_slot_div, void* y, int32_t y_dtype, int64_t y_slot_stride, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* ---- tensor-parallel exchange over NVLink peer memory (replaces the NCCL all-reduce blazr's TP would issue after
+ * the row-parallel o_proj / down_proj, reference src/engine/tensor_parallel.rs:125-160).
+ * One process per GPU: create on every rank, all-gather the 64-byte IPC handles, connect.  b200q_allreduce_f64 sums
+ * the ranks' f64 partial sums (b200q_matmul_q8 with y_dtype = B200Q_F64) in rank order and rounds once to f32, so the
+ * result is identical on every rank and equal to the 1-GPU output.  Graph-capturable, no host sync. */
+typedef struct b200q_comm b200q_comm;
+int32_t b200q_comm_create(int32_t rank, int32_t world, int64_t max_elems, int32_t device, b200q_comm** out);
+int32_t b200q_comm_handle(const b200q_comm* c, void* out64);
+int32_t b200q_comm_connect(b200q_comm* c, const void* handles /* world x 64 bytes, rank order */);
+int32_t b200q_allreduce_f64(b200q_comm* c, const double* src, float* dst, int64_t n, void* stream);
+int32_t b200q_comm_free(b200q_comm* c);
 
 /* Decode matmuls with a fused activation producer (M <= 4): the consumer warps build the quantised activation in
  * shared memory while the first weight chunks are in flight, so no separate norm / SwiGLU kernel runs.

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from blazr_b200 import decode, ops
+from blazr_b200 import decode, ops, synth
 from oracle.model import OracleModel
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
@@ -95,3 +95,25 @@ def test_greedy_stream_llama32_1b_shape_q4km(client):
     cfg = decode.PRESETS["small-1b"]
     prompt = list(range(10, 42))
     _check_greedy(client, cfg, "Q4_K_M", prompt, 128, range(1, 4), 192)
+
+
+def test_peer_allreduce_world1_and_f64_partials(client):
+    """the TP exchange path on one GPU: the matvec's f64 partial output rounds to exactly its f32 output, and the
+    one-shot all-reduce with world = 1 (push to self, flag, ordered sum) reproduces it; repeated calls exercise the
+    epoch / parity protocol"""
+    import ctypes as C
+    t = synth.GGML["Q6_K"]
+    N, K = 1024, 2048
+    w = client.weight_from_ggml(t, synth.random_ggml(t, N, K, seed=5), N, K)
+    x = torch.from_numpy(synth.random_act(2, K, seed=6)).cuda()
+    xq = client.quantize_act(x)
+    y32 = client.matmul_q8(xq, 2, w)
+    y64 = client.matmul_q8(xq, 2, w, out=torch.empty((2, N), dtype=torch.float64, device="cuda"))
+    assert torch.equal(y64.to(torch.float32), y32)
+    comm = ops.PeerComm(0, 1, 2 * N, client.device)
+    out = torch.empty((2, N), dtype=torch.float32, device="cuda")
+    for _ in range(5):
+        out.zero_()
+        comm.allreduce_f64(y64, out)
+        assert torch.equal(out, y32)
+    comm.free()

@@ -23,6 +23,8 @@ for scheme in ("Q4_K_M", "Q8_0", "AWQ"):
         lref = ref_dec.logits[0].cpu().numpy()
         same = bool(np.array_equal(got, ref))
         err = float(np.abs(logits_tp - lref).max() / np.abs(lref).max())
+        bits = float((logits_tp.view(np.uint32) != lref.view(np.uint32)).mean())
+        print(f"tp{world} {scheme}: exchange={'peer-memory one-shot' if dec.comm is not None else 'NCCL'} logits differing in any bit: {bits:.2e}", flush=True)
         print(f"tp{world} {scheme}: greedy stream equal={same} first mismatch={int(np.nonzero(got != ref)[0][0]) if not same else -1} last-step logits rel err={err:.2e}", flush=True)
         ok = ok and (same or err < 1e-4)
     dist.barrier()
