@@ -343,6 +343,30 @@ def extras(client, cfg, scheme, pk):
                      "GBs": ws[0].canonical_bytes / (us * 1e-6) / 1e9, "includes": "f16 activation staging kernel + tcgen05 GEMM"}
     for w in ws:
         w.free()
+    # whole-step batched decode (BASELINE metric: "decode tok/s at batch 1 and batch 32"): 32 sequences, every
+    # projection on the tcgen05 path, replayed from one CUDA graph
+    try:
+        B = 32
+        decb = decode.Decoder(client, cfg, scheme, batch=B, max_ctx=96)
+        decb.capture()
+        decb.reset([1] * B)
+        for _ in range(8):
+            decb.graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 24
+        e0.record()
+        for _ in range(steps):
+            decb.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        msb = e0.elapsed_time(e1) / steps
+        out["decode_batch32_step"] = {"tokens_per_s": B / (msb * 1e-3), "ms_per_step": msb, "launches_per_step": decb.launches_per_step(),
+                                      "step_frac_hbm": decb.weight_bytes / (msb * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                      "what": f"{cfg.name} {scheme} batch-32 greedy decode, whole step (graph replay), context 9..32"}
+        del decb
+    except Exception as ex:  # secondary number: never take the headline down with it
+        out["decode_batch32_step"] = {"error": repr(ex)[:200]}
     return out
 
 

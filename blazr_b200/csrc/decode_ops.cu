@@ -95,14 +95,14 @@ __global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float*
     h_out[(size_t)m * H + k] = mine;
     const float v = __fmul_rn(__fmul_rn(mine, inv), wk);
     if (xnorm) xnorm[(size_t)m * H + k] = v;
-    quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
+    if (xq) quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
 }
 
 // ------------------------------------------------------------------------------------------------
 // act = silu(gate) * up ; xq = quant(act)       gate_up: [M, 2*F] (gate first), F % 32 == 0; the records are
 // zero-padded up to the next multiple of 256 (DeepSeek-V2-Lite experts: F = 1408 = 5.5 chunks)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restrict__ gu, int F, int M, uint8_t* __restrict__ xq) {
+__global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restrict__ gu, int F, int M, uint8_t* __restrict__ xq, float* __restrict__ act) {
     pdl_launch_dependents();
     pdl_wait();
     const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restri
     if (k < F) {
         const float g = gu[(size_t)m * 2 * F + k], u = gu[(size_t)m * 2 * F + F + k];
         v = __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, det_expf(-g))), u);
+        if (act) act[(size_t)m * F + k] = v;
     }
-    quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
+    if (xq) quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
         outv = __fdiv_rn((float)o, den);
         if (attn_out) attn_out[(size_t)m * nh * HD + (size_t)head * HD + t] = outv;
         // quantise this head's HD outputs into the o_proj activation records (32-blocks never straddle heads)
+        if (!xq) return;  // batched decode: the projection takes attn_out (f32)
         const int kglob = head * HD + t;
         const int kc = kglob / CHUNK_K, tin = kglob % CHUNK_K;
         uint8_t* rec = xq + ((size_t)kc * M + m) * ACT_REC_BYTES;
@@ -341,7 +343,7 @@ extern "C" {
 
 int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_out, const float* w, float eps, int64_t H, int64_t M, void* xq,
                                 float* xnorm, void* stream) {
-    if (!h_in || !h_out || !w || !xq || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
+    if (!h_in || !h_out || !w || (!xq && !xnorm) || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
     if (delta && h_in == h_out) return B200Q_ERR_INVALID_ARG;  // CTAs re-read the whole input row: no in-place update
     cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)(H / CHUNK_K), (unsigned)M), dim3(NORM_NT), 0, (cudaStream_t)stream, h_in, delta,
                                h_out, w, eps, (int)H, (int)M, (uint8_t*)xq, xnorm);
@@ -351,13 +353,21 @@ int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_
 int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream) {
     if (!gate_up || !xq || F <= 0 || F % 32 || M <= 0 || M > 65535) return B200Q_ERR_INVALID_ARG;
     cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)((F + CHUNK_K - 1) / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
-                               (int)M, (uint8_t*)xq);
+                               (int)M, (uint8_t*)xq, (float*)nullptr);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+/* batched decode (M > 4: the projections run on the tcgen05 path and take f32 activations): act[M, F] = silu(gate) * up */
+int32_t b200q_swiglu_f32(const float* gate_up, int64_t F, int64_t M, float* act, void* stream) {
+    if (!gate_up || !act || F <= 0 || F % 32 || M <= 0 || M > 65535) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)((F + CHUNK_K - 1) / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
+                               (int)M, (uint8_t*)nullptr, act);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }
 
 int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table, int32_t n_heads,
                           int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq, float* attn_out, void* stream) {
-    if (!qkv || !pos || !cache_k || !cache_v || !rope_table || !xq || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || M <= 0 || max_ctx <= 0)
+    if (!qkv || !pos || !cache_k || !cache_v || !rope_table || (!xq && !attn_out) || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || M <= 0 || max_ctx <= 0)
         return B200Q_ERR_INVALID_ARG;
     if (((int64_t)n_heads * head_dim) % CHUNK_K) return B200Q_ERR_INVALID_ARG;
     if ((size_t)max_ctx * 4 > 160 * 1024) return B200Q_ERR_UNSUPPORTED;

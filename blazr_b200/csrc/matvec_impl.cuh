@@ -127,7 +127,7 @@ __device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* x
     named_bar_sync(4, NT);  // records visible to every consumer warp
 }
 
-template <class F, int MB, bool PRO>
+template <class F, int MB, bool PRO, bool GRP>
 __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             const uint64_t pol = policy_evict_first();
             const uint32_t xbytes = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
             const uint32_t wbytes = (uint32_t)p.chunk_bytes;
-            const bool grouped = p.w_table != nullptr;
+            constexpr bool grouped = GRP;  // expert-bank launch (compile-time: the plain matvec carries none of it)
             const int64_t cpw = (int64_t)p.tpw * p.KC;  // grouped: chunks per weight
             if (grouped) pdl_wait();                      // the expert selection is produced by the preceding kernel
             // j-th processed chunk -> (weight address, activation record address)
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
             // last arriver: sum the partials in CTA order (deterministic).  Every load of a batch of NB contributors
             // x all passes is issued before the first add, so the reduction costs one L2 round trip per NB contributors.
-            const int64_t tql = p.w_table ? tq % p.tpw : tq;                      // tile index inside its weight
-            const int64_t ybase = p.w_table ? (tq / p.tpw) * p.y_slot_stride : 0;  // grouped: output of slot tq / tpw
+            const int64_t tql = GRP ? tq % p.tpw : tq;                      // tile index inside its weight
+            const int64_t ybase = GRP ? (tq / p.tpw) * p.y_slot_stride : 0;  // grouped: output of slot tq / tpw
             constexpr int PASSES = 2 * MB;                       // 64 doubles (one double2 per lane) per pass
             constexpr int NB = MB == 1 ? 8 : (MB == 2 ? 4 : 2);  // contributors in flight
             double2 sum[PASSES];
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             bsA[m] = (int)(int16_t)(bs & 0xFFFFu);
             bsB[m] = (int)(int16_t)(bs >> 16);
         }
-        const bool skip_chunk = p.w_table != nullptr && *reinterpret_cast<const volatile int*>(wc + p.chunk_bytes + p.M * ACT_REC_BYTES) != 0;
+        const bool skip_chunk = GRP && *reinterpret_cast<const volatile int*>(wc + p.chunk_bytes + p.M * ACT_REC_BYTES) != 0;
         if (!(p.debug_flags & 1) && !skip_chunk)
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++) {
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         if (seg == 2) {
             if (i == 0) {
 #pragma unroll
-                const int64_t tl = p.w_table ? t % p.tpw : t;
-                const int64_t ybase = p.w_table ? (int64_t)(t / p.tpw) * p.y_slot_stride : 0;
+                const int64_t tl = GRP ? t % p.tpw : t;
+                const int64_t ybase = GRP ? (int64_t)(t / p.tpw) * p.y_slot_stride : 0;
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
                     const int64_t n = tl * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
                     if (n < p.N) {
@@ -439,13 +439,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }
 
-template <class F, int MB, bool PRO>
+template <class F, int MB, bool PRO, bool GRP>
 static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStream_t st) {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -459,7 +459,7 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO>, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP>, p);
     if (le != cudaSuccess) return le;
     count_launch();
     return cudaGetLastError();
@@ -467,10 +467,11 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
 
 template <class F>
 static cudaError_t launch_f(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
+    if (p.w_table) return mb == 1 && !p.pro ? launch_t<F, 1, false, true>(p, grid, smem, st) : cudaErrorInvalidValue;
     switch (mb) {
-        case 1: return p.pro ? launch_t<F, 1, true>(p, grid, smem, st) : launch_t<F, 1, false>(p, grid, smem, st);
-        case 2: return p.pro ? launch_t<F, 2, true>(p, grid, smem, st) : launch_t<F, 2, false>(p, grid, smem, st);
-        case 4: return p.pro ? launch_t<F, 4, true>(p, grid, smem, st) : launch_t<F, 4, false>(p, grid, smem, st);
+        case 1: return p.pro ? launch_t<F, 1, true, false>(p, grid, smem, st) : launch_t<F, 1, false, false>(p, grid, smem, st);
+        case 2: return p.pro ? launch_t<F, 2, true, false>(p, grid, smem, st) : launch_t<F, 2, false, false>(p, grid, smem, st);
+        case 4: return p.pro ? launch_t<F, 4, true, false>(p, grid, smem, st) : launch_t<F, 4, false, false>(p, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }

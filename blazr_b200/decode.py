@@ -168,7 +168,11 @@ class Decoder:
 
     def __init__(self, client: ops.B200Client, cfg: ModelConfig, scheme: str, batch: int = 1, max_ctx: int = 512,
                  host: Optional[HostModel] = None, seed: int = 0xB200, tp_rank: int = 0, tp_world: int = 1, group=None):
-        assert 1 <= batch <= 4, "the dp4a decode path handles M <= 4 (batched decode uses the GEMM path)"
+        assert 1 <= batch <= 256
+        # M <= 4: dp4a matvec on int8 activation records (bit-exact contract); M > 4 (batched decode, reference
+        # src/engine/batch_decode.rs:115-147): tcgen05 dequant-GEMM on f32 activations (1e-2 tolerance contract)
+        self.wide = batch > 4
+        assert not (self.wide and tp_world > 1), "batched decode is single-GPU in this round"
         self.c, self.cfg, self.scheme, self.M, self.max_ctx = client, cfg, scheme, batch, max_ctx
         self.rank, self.world, self.group = tp_rank, tp_world, group
         dev = client.device
@@ -224,11 +228,14 @@ class Decoder:
         self.logits = self.logits_local if tp_world == 1 else torch.zeros((tp_world, M, v1 - v0), **f32)
         self.ids = torch.zeros(M, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(M, dtype=torch.int32, device=dev)
-        act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
-        self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
+        if self.wide:
+            self.xq_h, self.xq_attn, self.xq_ff = (torch.zeros((M, k), **f32) for k in (H, self.qd, self.ff))  # f32 activations
+        else:
+            act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
+            self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
         import os as _os
-        self.fused = _os.environ.get("B200Q_FUSED", "0") != "0"   # add+norm+quant fused into the matvec prologue
-        self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0"  # measured slower: 148x redundant SiLU
+        self.fused = _os.environ.get("B200Q_FUSED", "0") != "0" and not self.wide   # add+norm+quant fused into the matvec prologue
+        self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0" and not self.wide  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
         # tensor parallel: one-shot NVLink all-reduce of the f64 partial sums (csrc/comm.cu); B200Q_TP_NCCL=1 falls back
@@ -312,6 +319,12 @@ class Decoder:
         L = ops.lib()
         st = ops._stream_ptr(self.dev)
         dt = ops.F64 if out.dtype == torch.float64 else ops.F32
+        if self.wide:
+            for ln in lins:
+                ops._check(L.b200q_matmul(ln.w.handle, C.c_void_p(xq.data_ptr()), C.c_int32(ops.F32), C.c_int64(self.M), C.c_int64(xq.stride(0)),
+                                          C.c_void_p(out.data_ptr() + 4 * ln.col0), C.c_int32(ops.F32), C.c_int64(out.stride(0)),
+                                          C.c_void_p(ln.ws.data_ptr()), C.c_size_t(ln.ws.numel()), st))
+            return
         for ln in lins:
             ops._check(L.b200q_matmul_q8(ln.w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(self.M),
                                          C.c_void_p(out.data_ptr() + out.element_size() * ln.col0), C.c_int32(dt), C.c_int64(out.stride(0)),
@@ -345,7 +358,8 @@ class Decoder:
         def norm(w):
             nonlocal hin, hout
             ops._check(L.b200q_add_rmsnorm_quant(P(hin), P(delta) if delta is not None else None, P(hout), P(w), C.c_float(cfg.eps),
-                                                 C.c_int64(cfg.hidden), C.c_int64(M), P(self.xq_h), None, st))
+                                                 C.c_int64(cfg.hidden), C.c_int64(M), None if self.wide else P(self.xq_h),
+                                                 P(self.xq_h) if self.wide else None, st))
             hin, hout = hout, hin
 
         def matvec_norm(lins, w, out):
@@ -366,7 +380,7 @@ class Decoder:
                 self._matvec(lay["qkv"], self.xq_h, self.qkv)
             ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
                                            C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
-                                           P(self.xq_attn), None, st))
+                                           None if self.wide else P(self.xq_attn), P(self.xq_attn) if self.wide else None, st))
             self._rowpar(lay["o"], self.xq_attn, self.delta)
             delta = self.delta
             if fused:
@@ -382,7 +396,10 @@ class Decoder:
                 self._allreduce(self.delta2)
                 delta = self.delta2
             else:
-                ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
+                if self.wide:
+                    ops._check(L.b200q_swiglu_f32(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
+                else:
+                    ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
                 self._rowpar(lay["down"], self.xq_ff, self.delta2)
                 delta = self.delta2
         if fused:
@@ -400,6 +417,8 @@ class Decoder:
             ops._check(L.b200q_argmax(P(self.logits), C.c_int64(self.logits.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
 
     def launches_per_step(self) -> int:
+        if getattr(self, "_launches", None):
+            return self._launches  # counted by the library during the un-captured warm-up step
         glue = 0 if self.fused else 1
         sw = 0 if self.fused_swiglu else 1
         n = 1 + glue + len(self.head) + 1  # embed, (final norm), head, argmax
@@ -411,7 +430,9 @@ class Decoder:
 
     def capture(self):
         """capture one decode step into a CUDA graph (reference src/engine/cuda_graphs.rs:124-130)"""
+        n0 = ops.launch_count()
         self.step()  # un-captured warm-up forward (cuda_graphs.rs:104)
+        self._launches = ops.launch_count() - n0
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(self.dev)

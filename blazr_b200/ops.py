@@ -55,7 +55,7 @@ EXPORTS = [
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
     "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
-    "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free",
+    "b200q_swiglu_f32", "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free",
     "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
 ]
 

@@ -204,6 +204,9 @@ int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_
                                 void* xq, float* xnorm, void* stream);
 /* xq = quant(silu(gate) * up) for gate_up[M, 2F] (gate first) */
 int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream);
+/* batched decode (M > 4, tcgen05 path takes f32 activations): act[M, F] = silu(gate) * up.  The norm and attention
+ * operators likewise accept xq == NULL when their f32 output (xnorm / attn_out) is requested instead. */
+int32_t b200q_swiglu_f32(const float* gate_up, int64_t F, int64_t M, float* act, void* stream);
 /* RoPE (adjacent pairs; cos/sin from rope_table [max_ctx][hd/2][2] f32) on q and the new k, KV append at pos[m],
  * single-query attention (f64 reductions, deterministic exp), quantised output.
  * qkv[M,(nh+2nkv)*hd] f32; caches [M][max_ctx][nkv][hd] f32; attn_out (nullable) receives the f32 result */

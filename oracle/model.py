@@ -14,23 +14,36 @@ import oracle
 
 
 class OracleLinear:
-    def __init__(self, hl):
-        """hl: blazr_b200.decode.HostLinear"""
+    def __init__(self, hl, flavour: str = "B"):
+        """hl: blazr_b200.decode.HostLinear.  flavour "B" = int8 activations + integer dots (the decode contract),
+        "A" = dequantized f32 weights x f32 activations in f64 (the reference's f32 CPU path; tolerance contract)"""
         self.N, self.K = hl.N, hl.K
         self.perm = None
+        self.flavour = flavour
         if hl.fmt in oracle.GGML_TYPES:
             t = oracle.GGML_TYPES[hl.fmt]
-            self.qi, self.a, self.b, self.sub = oracle.decompose_ggml(t, hl.data, hl.N, hl.K)
+            if flavour == "A":
+                self.deq = oracle.dequant_ggml(t, hl.data, hl.N, hl.K)
+            else:
+                self.qi, self.a, self.b, self.sub = oracle.decompose_ggml(t, hl.data, hl.N, hl.K)
         elif hl.fmt == "AWQ":
             qw, sc, zr, gs = hl.data
-            self.qi, self.a, self.b, self.sub = oracle.awq_decompose(qw, sc, zr, gs)
+            if flavour == "A":
+                self.deq = oracle.awq_dequant(qw, sc, zr, gs)
+            else:
+                self.qi, self.a, self.b, self.sub = oracle.awq_decompose(qw, sc, zr, gs)
         elif hl.fmt == "GPTQ":
             qw, sc, qz, gi, gs = hl.data
-            self.qi, self.a, self.b, self.sub, self.perm = oracle.gptq_decompose(qw, sc, qz, None, gs, 1)
+            if flavour == "A":
+                self.deq = oracle.gptq_dequant(qw, sc, qz, None, gs, 1)
+            else:
+                self.qi, self.a, self.b, self.sub, self.perm = oracle.gptq_decompose(qw, sc, qz, None, gs, 1)
         else:
             raise ValueError(hl.fmt)
 
     def __call__(self, x: np.ndarray) -> np.ndarray:
+        if self.flavour == "A":
+            return oracle.matmul_dense(self.deq, x)
         return oracle.matmul_q8(self.qi, self.a, self.b, self.sub, x)
 
 
@@ -65,15 +78,15 @@ def rope_pairs(x: np.ndarray, cs: np.ndarray) -> np.ndarray:
 
 
 class OracleModel:
-    def __init__(self, host):
+    def __init__(self, host, flavour: str = "B"):
         """host: blazr_b200.decode.HostModel"""
         self.cfg = host.cfg
         self.embed = host.embed
         self.layers = []
         for lay in host.layers:
-            self.layers.append({k: (OracleLinear(v) if k in ("q", "k", "v", "o", "gate", "up", "down") else v) for k, v in lay.items()})
+            self.layers.append({k: (OracleLinear(v, flavour) if k in ("q", "k", "v", "o", "gate", "up", "down") else v) for k, v in lay.items()})
         self.final_norm = host.final_norm
-        self.head = OracleLinear(host.lm_head)
+        self.head = OracleLinear(host.lm_head, flavour)
         self.rope = rope_table(4096, self.cfg.head_dim, self.cfg.rope_theta)
         self.reset()
 
