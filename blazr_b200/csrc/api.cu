@@ -43,6 +43,10 @@ static bool ggml_family(int ggml_type, FamilyInfo* fi) {
         case 12: *fi = {B200Q_FAM_Q4_K, 256, 144, 32, 128 * 144}; return true;
         case 14: *fi = {B200Q_FAM_Q6_K, 256, 210, 16, 128 * 210}; return true;
         case 8: *fi = {B200Q_FAM_Q8_0, 32, 34, 32, 128 * 272}; return true;
+        // source adaptors (formats.cuh): exact re-encodings into an existing family at upload
+        case 2: *fi = {B200Q_FAM_G4, 32, 18, 32, 128 * 128 + 128 * 8 * 3}; return true;   // Q4_0  -> G4, 32-wide groups
+        case 6: *fi = {B200Q_FAM_Q8_0, 32, 22, 32, 128 * 272}; return true;               // Q5_0  -> Q8_0 family
+        case 20: *fi = {B200Q_FAM_Q8_0, 32, 18, 32, 128 * 272}; return true;              // IQ4_NL -> Q8_0 family
         default: return false;
     }
 }
@@ -158,7 +162,8 @@ int32_t b200q_weight_from_ggml_shard(int32_t ggml_type, const void* blocks, int3
     w->source = B200Q_SRC_GGML;
     w->ggml_type = ggml_type;
     w->sub = fi.sub;
-    w->gpc = 1;
+    w->gpc = ggml_type == 2 ? 8 : 1;
+    w->group_size = ggml_type == 2 ? 32 : 0;
     w->chunk_bytes = fi.chunk_bytes;
     w->canonical_bytes = w->N * (w->K / fi.block_elems) * fi.block_bytes;
     int32_t rc = alloc_weight(w, device);

@@ -274,6 +274,92 @@ struct FmtG4 {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Source adaptors: 32-element ggml block formats whose arithmetic is exactly expressible in an existing family are
+// re-encoded at upload and then run that family's kernels (no new compute code, dequantized weights and integer
+// partials stay bit-exact):
+//   Q4_0   w = d (q - 8)          -> G4 with 32-wide groups: scale d, integer zero point 8          (4.75 bit/weight on device)
+//   Q5_0   w = d (q5 - 16)        -> Q8_0 family: int8 = q5 - 16, same d                            (8.5 bit/weight on device)
+//   IQ4_NL w = d kvalues[q]       -> Q8_0 family: int8 = kvalues[q] (non-linear 4-bit codebook)     (8.5 bit/weight on device)
+// Only repack_row differs; chunk_bytes forwards to the family.
+// ------------------------------------------------------------------------------------------------
+struct SrcQ4_0 {
+    __host__ __device__ static constexpr int chunk_bytes(int gpc) { return FmtG4::chunk_bytes(gpc); }
+    __host__ __device__ static constexpr int src_block_elems() { return 32; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 18; }
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta meta) {
+        uint8_t q[256];
+        uint16_t sc[8];
+        uint8_t z[8];
+        for (int blk = 0; blk < 8; blk++) {
+            const uint8_t* s = src + 18 * blk;
+            const bool ok = blk < nvalid;
+            sc[blk] = ok ? (uint16_t)(s[0] | (s[1] << 8)) : (uint16_t)0;
+            z[blk] = ok ? 8 : 0;
+            for (int j = 0; j < 16; j++) {
+                q[32 * blk + j] = ok ? (s[2 + j] & 0xF) : 0;
+                q[32 * blk + 16 + j] = ok ? (s[2 + j] >> 4) : 0;
+            }
+        }
+        FmtG4::store_row(q, sc, z, chunk, r, meta.gpc);
+    }
+};
+
+__device__ __forceinline__ void store_q8_family_row(const int8_t (*vals)[32], const uint16_t* d, uint8_t* chunk, int r) {
+    uint8_t* qs = chunk + FmtQ8_0::QS + r * 256;
+    uint8_t* dd = chunk + FmtQ8_0::D + r * 16;
+    for (int blk = 0; blk < 8; blk++) {
+        dd[2 * blk] = (uint8_t)(d[blk] & 0xFF);
+        dd[2 * blk + 1] = (uint8_t)(d[blk] >> 8);
+        for (int h = 0; h < 2; h++) {
+            uint8_t* dst = qs + 16 * swz8(r, 2 * blk + h);
+            for (int b = 0; b < 16; b++) dst[b] = (uint8_t)vals[blk][16 * h + b];
+        }
+    }
+}
+
+struct SrcQ5_0 {
+    __host__ __device__ static constexpr int chunk_bytes(int gpc) { return FmtQ8_0::chunk_bytes(gpc); }
+    __host__ __device__ static constexpr int src_block_elems() { return 32; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 22; }
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        int8_t v[8][32];
+        uint16_t d[8];
+        for (int blk = 0; blk < 8; blk++) {
+            const uint8_t* s = src + 22 * blk;
+            const bool ok = blk < nvalid;
+            d[blk] = ok ? (uint16_t)(s[0] | (s[1] << 8)) : (uint16_t)0;
+            const uint32_t qh = ok ? ((uint32_t)s[2] | ((uint32_t)s[3] << 8) | ((uint32_t)s[4] << 16) | ((uint32_t)s[5] << 24)) : 0u;
+            for (int j = 0; j < 16; j++) {
+                v[blk][j] = ok ? (int8_t)(((s[6 + j] & 0xF) | (((qh >> j) & 1) << 4)) - 16) : (int8_t)0;
+                v[blk][j + 16] = ok ? (int8_t)(((s[6 + j] >> 4) | (((qh >> (j + 16)) & 1) << 4)) - 16) : (int8_t)0;
+            }
+        }
+        store_q8_family_row(v, d, chunk, r);
+    }
+};
+
+struct SrcIQ4NL {
+    __host__ __device__ static constexpr int chunk_bytes(int gpc) { return FmtQ8_0::chunk_bytes(gpc); }
+    __host__ __device__ static constexpr int src_block_elems() { return 32; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 18; }
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        const int8_t kv[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};  // public ggml codebook
+        int8_t v[8][32];
+        uint16_t d[8];
+        for (int blk = 0; blk < 8; blk++) {
+            const uint8_t* s = src + 18 * blk;
+            const bool ok = blk < nvalid;
+            d[blk] = ok ? (uint16_t)(s[0] | (s[1] << 8)) : (uint16_t)0;
+            for (int j = 0; j < 16; j++) {
+                v[blk][j] = ok ? kv[s[2 + j] & 0xF] : (int8_t)0;
+                v[blk][j + 16] = ok ? kv[s[2 + j] >> 4] : (int8_t)0;
+            }
+        }
+        store_q8_family_row(v, d, chunk, r);
+    }
+};
+
 // signed byte e (0..31) of a unit
 __device__ __forceinline__ int unit_elem(const Unit& u, int e) { return (int)(int8_t)((u.v[e >> 2] >> (8 * (e & 3))) & 0xFF); }
 

@@ -7,6 +7,16 @@ namespace b200q {
 cudaError_t launch_repack_ggml(int family, const uint8_t* src, int64_t src_row_bytes, int64_t n0, int64_t k0, const b200q_weight* w,
                                cudaStream_t st) {
     (void)family;
+    // source adaptors (formats.cuh): ggml types re-encoded into an existing family
+    if (w->ggml_type == 2 || w->ggml_type == 6 || w->ggml_type == 20) {
+        dim3 grid((unsigned)w->KC, (unsigned)w->T);
+        const FmtMeta meta{w->gpc};
+        if (w->ggml_type == 2) repack_ggml_kernel<SrcQ4_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else if (w->ggml_type == 6) repack_ggml_kernel<SrcQ5_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else repack_ggml_kernel<SrcIQ4NL><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        count_launch();
+        return cudaGetLastError();
+    }
     switch (w->family) {
         case B200Q_FAM_Q4_K: return repack_launch<B200Q_FAM_Q4_K>(src, src_row_bytes, n0, k0, w, st);
         case B200Q_FAM_Q6_K: return repack_launch<B200Q_FAM_Q6_K>(src, src_row_bytes, n0, k0, w, st);

@@ -190,7 +190,8 @@ class Decoder:
         self.layers = []
         M = batch
         for i in range(cfg.n_layers):
-            fm = layer_formats(cfg, scheme, i)
+            # formats come from the weights themselves when a host model (tests, GGUF files) is given
+            fm = {p_: host.layers[i][p_].fmt for p_ in ("q", "k", "v", "o", "gate", "up", "down")} if host else layer_formats(cfg, scheme, i)
             lay = {}
             # column-parallel q | k | v (rows of this rank's heads), fused where formats agree
             lay["qkv"] = self._fused(i, [("q", fm["q"], cfg.n_heads * hd, pl.q_rows[0], self.qd),
@@ -209,7 +210,7 @@ class Decoder:
             self.layers.append(lay)
         self.final_norm = torch.from_numpy(host.final_norm if host else np.ones(H, np.float32)).to(dev)
         self.rope = torch.from_numpy(rope_table(max_ctx, hd, cfg.rope_theta)).to(dev)
-        self.head = self._fused(-1, [("lm_head", head_format(scheme), cfg.vocab, v0, v1 - v0)], H, host)
+        self.head = self._fused(-1, [("lm_head", host.lm_head.fmt if host else head_format(scheme), cfg.vocab, v0, v1 - v0)], H, host)
         if host is not None:
             self.embed = torch.from_numpy(host.embed).to(dev)
         else:

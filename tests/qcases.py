@@ -6,7 +6,7 @@ import numpy as np
 import oracle
 from blazr_b200 import ops, synth
 
-GGML_GPU = ["Q4_K", "Q6_K", "Q8_0"]
+GGML_GPU = ["Q4_K", "Q6_K", "Q8_0", "Q4_0", "Q5_0", "IQ4_NL"]  # the last three run as exact re-encodings (formats.cuh adaptors)
 INT4 = ["AWQ", "GPTQ", "GPTQ_ACT", "GPTQ_Z0", "AWQ_G64"]
 ALL = GGML_GPU + INT4
 

@@ -145,3 +145,22 @@ def test_batched_decode_gemm_path_matches_oracle_logits(client, scheme):
     dec2 = decode.Decoder(client, cfg, scheme, batch=8, max_ctx=64, host=hm)
     out = dec2.generate(prompts, 2, use_graph=True)
     assert out.shape == (8, 2)
+
+
+def test_load_gguf_file_and_decode(client, tmp_path):
+    """a GGUF file (written by the independent gguf package) -> parse -> upload raw blocks ->
+    decode; the greedy stream equals the oracle's on the same weights (tied-embedding variant included: lm_head =
+    token_embd stored as Q6_K and expanded through DequantOps for the embedding lookup)."""
+    from blazr_b200 import gguf_loader
+    from gguf_util import write_gguf
+    hm = decode.build_host_model(decode.PRESETS["tiny"], "Q4_K_M", seed=21)
+    path = str(tmp_path / "tiny.gguf")
+    write_gguf(path, hm)
+    dec, cfg = gguf_loader.load_gguf(client, path, max_ctx=64)
+    assert cfg.vocab == hm.cfg.vocab
+    prompt = np.asarray([[5, 3, 8, 1]])
+    got = dec.generate(prompt, 24, use_graph=True)[0]
+    toks, gaps = OracleModel(hm).generate(prompt[0], 24)
+    if not np.array_equal(got, toks):
+        j = int(np.nonzero(got != toks)[0][0])
+        assert gaps[j] < NEAR_TIE
