@@ -225,8 +225,14 @@ class Decoder:
         self.delta2 = torch.zeros((M, H), **f32)  # down_proj output (the fused o->norm reads delta while down writes)
         self.qkv = torch.zeros((M, self.qd + 2 * self.kvd), **f32)
         self.gu = torch.zeros((M, 2 * self.ff), **f32)
-        self.logits_local = torch.zeros((M, v1 - v0), **f32)
-        self.logits = self.logits_local if tp_world == 1 else torch.zeros((tp_world, M, v1 - v0), **f32)
+        if tp_world == 1:
+            self.logits_local = torch.zeros((M, v1 - v0), **f32)
+            self.logits = self.logits_local
+        else:
+            assert v1 > v0, "vocabulary too small for this TP degree"
+            vs = tp.vocab_shard_rows(cfg.vocab, tp_world)   # same on every rank; columns beyond this rank's rows stay -inf
+            self.logits_local = torch.full((M, vs), float("-inf"), **f32)
+            self.logits = torch.zeros((tp_world, M, vs), **f32)
         self.ids = torch.zeros(M, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(M, dtype=torch.int32, device=dev)
         if self.wide:
@@ -411,9 +417,9 @@ class Decoder:
             self._matvec(self.head, self.xq_h, self.logits_local)
         if self.world > 1:
             torch.distributed.all_gather_into_tensor(self.logits, self.logits_local, group=self.group)
-            full = self.logits.permute(1, 0, 2).reshape(M, -1).contiguous()  # ranks hold consecutive vocab slices
+            full = self.logits.permute(1, 0, 2).reshape(M, -1).contiguous()  # column r * vs + j = vocabulary id (padding = -inf)
             ops._check(L.b200q_argmax(P(full), C.c_int64(full.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
-            self._full_logits = full
+            self._full_logits = full[:, :cfg.vocab]
         else:
             ops._check(L.b200q_argmax(P(self.logits), C.c_int64(self.logits.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
 

@@ -31,6 +31,12 @@ class TpPlan:
     vocab_rows: Tuple[int, int]
 
 
+def vocab_shard_rows(vocab: int, world: int) -> int:
+    """rows of the logits buffer every rank contributes to the lm_head all-gather (128-row granularity)"""
+    per = -(-vocab // world)
+    return -(-per // 128) * 128
+
+
 def validate_tp_config(world: int, n_heads: int, n_kv_heads: int) -> None:
     """reference src/engine/tensor_parallel.rs:76-101"""
     if world <= 1:
@@ -46,7 +52,11 @@ def plan(hidden: int, n_heads: int, n_kv_heads: int, head_dim: int, ffn: int, vo
     h0, h1 = ops.shard_range(n_heads, rank, world)
     k0, k1 = ops.shard_range(n_kv_heads, rank, world)
     f0, f1 = ops.shard_range(ffn, rank, world, granule=256)
-    v0, v1 = ops.shard_range(vocab, rank, world, granule=128)
+    # lm_head: equal-size vocabulary shards (the all-gather of the logits needs the same count on every rank):
+    # rank r owns [r * vs, min((r + 1) * vs, V)), vs = ceil(V / world) rounded up to 128 rows; the last rank's shard is
+    # shorter and the tail of its logits buffer stays at -inf, so the gathered [world * vs] row indexes the vocabulary directly
+    vs = vocab_shard_rows(vocab, world)
+    v0, v1 = min(rank * vs, vocab), min((rank + 1) * vs, vocab)
     return TpPlan(rank, world, h1 - h0, k1 - k0, (h0 * head_dim, h1 * head_dim), (k0 * head_dim, k1 * head_dim),
                   (h0 * head_dim, h1 * head_dim), (f0, f1), (f0, f1), (v0, v1))
 

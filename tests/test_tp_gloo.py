@@ -134,3 +134,24 @@ def test_ep2_local_experts_all_reduce_over_gloo():
     assert ret[0][0] == (0, 4) and ret[1][0] == (4, 8)
     assert ret[0][1] < 1e-6 and ret[1][1] < 1e-6
     assert ret[0][2] + ret[1][2] == 6  # every routed slot is hosted by exactly one rank
+
+
+@pytest.mark.parametrize("vocab,world", [(32000, 2), (32000, 4), (32000, 8), (128256, 8), (128256, 4), (2048, 2), (102400, 8)])
+def test_vocab_shards_are_equal_sized_and_index_the_vocabulary(vocab, world):
+    """the lm_head all-gather needs the same element count on every rank (32000 / 8 at 128-row granularity is not even:
+    unequal shards hang NCCL): every rank contributes vocab_shard_rows columns, padding stays -inf, and the column index
+    of the gathered row is the vocabulary id"""
+    vs = tp.vocab_shard_rows(vocab, world)
+    assert vs % 128 == 0 and vs * world >= vocab
+    rng = np.random.Generator(np.random.PCG64(vocab + world))
+    logits = rng.standard_normal(vocab).astype(np.float32)
+    gathered = np.full((world, vs), -np.inf, dtype=np.float32)
+    covered = 0
+    for r in range(world):
+        pl = tp.plan(4096, 32, 8, 128, 14336, vocab, r, world)
+        v0, v1 = pl.vocab_rows
+        assert v0 == covered and v1 > v0 and v1 - v0 <= vs
+        gathered[r, :v1 - v0] = logits[v0:v1]
+        covered = v1
+    assert covered == vocab
+    assert int(np.argmax(gathered.reshape(-1))) == int(np.argmax(logits))

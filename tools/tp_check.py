@@ -8,9 +8,9 @@ from blazr_b200 import decode, ops
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-cfg = decode.PRESETS["tiny"]
+cfg = decode.PRESETS["tiny" if world <= 2 else "small-1b"]   # tiny has 2 kv heads; small-1b (32 heads / 8 kv) shards up to TP8
 ok = True
-for scheme in ("Q4_K_M", "Q8_0", "AWQ"):
+for scheme in (("Q4_K_M", "Q8_0", "AWQ") if world <= 2 else ("Q4_K_M",)):
     hm = decode.build_host_model(cfg, scheme, seed=2)
     client = ops.B200Client(local)
     dec = decode.Decoder(client, cfg, scheme, batch=1, max_ctx=96, host=hm, tp_rank=rank, tp_world=world)
