@@ -133,7 +133,9 @@ def run_reference(args):
         "metric": "decode_tokens_per_s", "value": toks, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * args.batch / toks, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4/6/8 -> f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{model} GGUF {scheme} random-init, batch-{args.batch} greedy decode (CPU path)", "l2": "n/a (CPU)"},
+        "config": {"workload": f"{model} GGUF {scheme} random-init, batch-{args.batch} greedy decode, {args.prompt}-token prompt then {args.steps} tokens",
+                   "parallelism": f"cpu x{cores} threads", "l2": "n/a (CPU path: weights streamed from host DRAM)",
+                   "note": "each step is a bounded sample: whole layers through the CPU port, scaled by weights to 7L+1 projections"},
         "cpu_baseline": {"value": toks, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": toks, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -144,6 +146,20 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def arm_watchdog(seconds: float, what: str):
+    """A multi-rank run that deadlocks (a collective with mismatched counts, a peer that died) must not hold the box:
+    after `seconds` rank 0 prints an error line in the bench's JSON shape and every rank leaves."""
+    def fire():
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": "decode_tokens_per_s", "value": None, "unit": "tokens/s", "impl": "b200",
+                              "error": f"watchdog: {what} did not finish within {seconds:.0f} s"}), flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -163,6 +179,7 @@ def run_b200(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     model, scheme = args.workload.split(":")
     cfg = decode.PRESETS[model]
+    watchdog = arm_watchdog(float(os.environ.get("B200Q_BENCH_WATCHDOG_S", "900")), f"bench.py --gpus {args.gpus} ({args.workload})")
     client = ops.B200Client(local)
     M = args.batch
     max_ctx = args.prompt + args.warmup + 2 * args.steps + 64
@@ -298,6 +315,7 @@ def run_b200(args):
         if extra:
             out["extra"] = extra
         print(json.dumps(out), flush=True)
+    watchdog.cancel()
     if world > 1:
         # NCCL kernels are baked into the captured graphs: drop the graphs, then leave without the collective
         # teardown (destroy_process_group can block on communicators that captured graphs still reference)
