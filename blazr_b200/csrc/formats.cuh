@@ -16,7 +16,11 @@
 // which is the decomposition the oracle uses (oracle/quant_oracle.c decompose_block), so dequantized weights
 // and integer partials are bit-comparable.
 #pragma once
+#ifdef B200Q_HOST_CHECK
+#include "hostcheck/host_shim.h"  // CPU build of the layout logic for tests/test_host_formats.py
+#else
 #include "common.cuh"
+#endif
 
 namespace b200q {
 
@@ -271,6 +275,310 @@ struct FmtG4 {
         u.a[0] = u.a[1] = s;
         u.b[0] = u.b[1] = 0.0f;
         u.off[0] = u.off[1] = z;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Formats added after the headline three ("the remaining K formats", BASELINE north_star).  Same micro-interface, so
+// every kernel (dequantize, integer partials, matvec, grouped matvec, tcgen05 GEMM) is instantiated unchanged.  Their
+// repack_row / load_unit are verified on the CPU against the oracle (hostcheck/, tests/test_host_formats.py).
+// High-bit planes are re-encoded so that word K of a unit gets its 4 bits with one shift + mask:
+//   hb' bit (8 c + K) = extra bit of element 4 K + c         (K = 0..7 unit words, c = 0..3 bytes)
+// and 2-bit payloads so that   v[4 h + kk] = (W[h] >> 2 kk) & 0x03030303   (h = 16-element half, kk = 0..3).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int swzw(int r, int i) { return i ^ ((r >> 2) & 7); }   // planes with one 4-byte word per unit (32 B rows)
+__device__ __forceinline__ int swzd(int r, int i) { return i ^ ((r >> 1) & 7); }   // planes with 8 bytes per unit (64 B rows)
+
+__device__ __forceinline__ uint32_t pack_hibits(const uint8_t* bit /*[32] 0/1*/) {
+    uint32_t w = 0;
+    for (int K = 0; K < 8; K++)
+        for (int c = 0; c < 4; c++) w |= (uint32_t)(bit[4 * K + c] & 1) << (8 * c + K);
+    return w;
+}
+__device__ __forceinline__ void store_u32(uint8_t* dst, uint32_t w) {
+    for (int c = 0; c < 4; c++) dst[c] = (uint8_t)(w >> (8 * c));
+}
+// 32 two-bit values -> 2 words (see above)
+__device__ __forceinline__ void store_2bit_unit(uint8_t* dst, const uint8_t* q /*[32]*/) {
+    for (int h = 0; h < 2; h++) {
+        uint32_t w = 0;
+        for (int kk = 0; kk < 4; kk++)
+            for (int c = 0; c < 4; c++) w |= (uint32_t)(q[16 * h + 4 * kk + c] & 3) << (8 * c + 2 * kk);
+        store_u32(dst + 4 * h, w);
+    }
+}
+
+// Q5_K : canonical [f16 d][f16 dmin][u8 s[12]][u8 qh[32]][u8 qs[128]]  (176 B / 256)
+// chunk: QS 128x128 B (low nibbles, unit order) | QH 128x32 B (hb' words) | HDR 128x16 B (as Q4_K)
+struct FmtQ5K {
+    static constexpr int FAMILY = 5, SUB = 32;
+    static constexpr bool NIB = false;
+    static constexpr bool SIGNED = false;
+    static constexpr bool HAS_MIN = true;
+    static constexpr int QS = 0, QH = 128 * 128, HDR = QH + 128 * 32;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 176; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 176; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* qs = chunk + QS + r * 128;
+        uint8_t* qh = chunk + QH + r * 32;
+        uint8_t* hdr = chunk + HDR + r * 16;
+        if (nvalid <= 0) {
+            for (int j = 0; j < 128; j++) qs[j] = 0;
+            for (int j = 0; j < 32; j++) qh[j] = 0;
+            for (int j = 0; j < 16; j++) hdr[j] = 0;
+            return;
+        }
+        for (int j = 0; j < 4; j++) hdr[j] = src[j];
+        const uint8_t* s = src + 4;
+        const uint8_t* H = src + 16;
+        const uint8_t* q = src + 48;
+        int sc[8], m[8];
+        for (int j = 0; j < 8; j++) k4_scale_min(j, s, sc[j], m[j]);
+        for (int j = 0; j < 8; j++) hdr[4 + j] = (uint8_t)(sc[j] | ((m[j] & 3) << 6));
+        for (int j = 0; j < 4; j++) hdr[12 + j] = (uint8_t)((m[2 * j] >> 2) | ((m[2 * j + 1] >> 2) << 4));
+        for (int i = 0; i < 8; i++) {
+            uint8_t v[32], hb[32];
+            const int c = i >> 1, hi = i & 1;
+            for (int l = 0; l < 32; l++) {
+                v[l] = hi ? (q[32 * c + l] >> 4) : (q[32 * c + l] & 0xF);
+                hb[l] = (H[l] >> (2 * c + hi)) & 1;
+            }
+            store_nib_unit(qs + 16 * swz8(r, i), v);
+            store_u32(qh + 4 * swzw(r, i), pack_hibits(hb));
+        }
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
+        const uint32_t hq = ld4(chunk + QH + r * 32 + 4 * swzw(r, i));
+        const uint32_t M4 = 0x0F0F0F0Fu, M1 = 0x01010101u;
+        u.v[0] = (w.x & M4) | (((hq >> 0) & M1) << 4); u.v[1] = (w.y & M4) | (((hq >> 1) & M1) << 4);
+        u.v[2] = (w.z & M4) | (((hq >> 2) & M1) << 4); u.v[3] = (w.w & M4) | (((hq >> 3) & M1) << 4);
+        u.v[4] = ((w.x >> 4) & M4) | (((hq >> 4) & M1) << 4); u.v[5] = ((w.y >> 4) & M4) | (((hq >> 5) & M1) << 4);
+        u.v[6] = ((w.z >> 4) & M4) | (((hq >> 6) & M1) << 4); u.v[7] = ((w.w >> 4) & M4) | (((hq >> 7) & M1) << 4);
+        const uint8_t* hdr = chunk + HDR + r * 16;
+        uint32_t dd = ld4(hdr);
+        float d = half_bits_to_float((uint16_t)(dd & 0xFFFF)), dmin = half_bits_to_float((uint16_t)(dd >> 16));
+        uint32_t b1 = hdr[4 + i], b2 = hdr[12 + (i >> 1)];
+        int sc = b1 & 63;
+        int m = (b1 >> 6) | (((b2 >> (4 * (i & 1))) & 0xF) << 2);
+        u.a[0] = u.a[1] = __fmul_rn(d, (float)sc);
+        u.b[0] = u.b[1] = __fmul_rn(dmin, (float)m);
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
+// Q4_1 : canonical 8 x [f16 d][f16 m][u8 qs[16]]  (160 B / 256),  w = d q + m
+// chunk: QS 128x128 B (block i's 16 bytes as stored: byte b = q[b] | q[16+b] << 4) | DM 128x32 B (8 x (d, m))
+struct FmtQ4_1 {
+    static constexpr int FAMILY = 7, SUB = 32;
+    static constexpr bool NIB = true;
+    static constexpr bool SIGNED = false;
+    static constexpr bool HAS_MIN = true;
+    static constexpr int QS = 0, DM = 128 * 128;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 160; }
+    __host__ __device__ static constexpr int src_block_elems() { return 32; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 20; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* qs = chunk + QS + r * 128;
+        uint8_t* dm = chunk + DM + r * 32;
+        for (int blk = 0; blk < 8; blk++) {
+            const uint8_t* s = src + 20 * blk;
+            const bool ok = blk < nvalid;
+            uint8_t* d4 = dm + 4 * swzw(r, blk);
+            for (int c = 0; c < 4; c++) d4[c] = ok ? s[c] : 0;
+            uint8_t* dst = qs + 16 * swz8(r, blk);
+            for (int b = 0; b < 16; b++) dst[b] = ok ? s[4 + b] : 0;
+        }
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
+        u.v[0] = w.x & 0x0F0F0F0Fu; u.v[1] = w.y & 0x0F0F0F0Fu; u.v[2] = w.z & 0x0F0F0F0Fu; u.v[3] = w.w & 0x0F0F0F0Fu;
+        if constexpr (RAWHI) {
+            u.v[4] = w.x & 0xF0F0F0F0u; u.v[5] = w.y & 0xF0F0F0F0u; u.v[6] = w.z & 0xF0F0F0F0u; u.v[7] = w.w & 0xF0F0F0F0u;
+        } else {
+            u.v[4] = (w.x >> 4) & 0x0F0F0F0Fu; u.v[5] = (w.y >> 4) & 0x0F0F0F0Fu;
+            u.v[6] = (w.z >> 4) & 0x0F0F0F0Fu; u.v[7] = (w.w >> 4) & 0x0F0F0F0Fu;
+        }
+        const uint32_t dm = ld4(chunk + DM + r * 32 + 4 * swzw(r, i));
+        u.a[0] = u.a[1] = half_bits_to_float((uint16_t)(dm & 0xFFFF));
+        u.b[0] = u.b[1] = -half_bits_to_float((uint16_t)(dm >> 16));
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
+// Q5_1 : canonical 8 x [f16 d][f16 m][u32 qh][u8 qs[16]]  (192 B / 256),  w = d q5 + m
+// chunk: QS 128x128 B | QH 128x32 B (hb' words) | DM 128x32 B
+struct FmtQ5_1 {
+    static constexpr int FAMILY = 9, SUB = 32;
+    static constexpr bool NIB = false;
+    static constexpr bool SIGNED = false;
+    static constexpr bool HAS_MIN = true;
+    static constexpr int QS = 0, QH = 128 * 128, DM = QH + 128 * 32;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 192; }
+    __host__ __device__ static constexpr int src_block_elems() { return 32; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 24; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* qs = chunk + QS + r * 128;
+        uint8_t* qh = chunk + QH + r * 32;
+        uint8_t* dm = chunk + DM + r * 32;
+        for (int blk = 0; blk < 8; blk++) {
+            const uint8_t* s = src + 24 * blk;
+            const bool ok = blk < nvalid;
+            uint8_t* d4 = dm + 4 * swzw(r, blk);
+            for (int c = 0; c < 4; c++) d4[c] = ok ? s[c] : 0;
+            const uint32_t h = ok ? ((uint32_t)s[4] | ((uint32_t)s[5] << 8) | ((uint32_t)s[6] << 16) | ((uint32_t)s[7] << 24)) : 0u;
+            uint8_t hb[32];
+            for (int e = 0; e < 32; e++) hb[e] = (h >> e) & 1;   // canonical: bit e of qh = 5th bit of element e
+            store_u32(qh + 4 * swzw(r, blk), pack_hibits(hb));
+            uint8_t* dst = qs + 16 * swz8(r, blk);
+            for (int b = 0; b < 16; b++) dst[b] = ok ? s[8 + b] : 0;
+        }
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
+        const uint32_t hq = ld4(chunk + QH + r * 32 + 4 * swzw(r, i));
+        const uint32_t M4 = 0x0F0F0F0Fu, M1 = 0x01010101u;
+        u.v[0] = (w.x & M4) | (((hq >> 0) & M1) << 4); u.v[1] = (w.y & M4) | (((hq >> 1) & M1) << 4);
+        u.v[2] = (w.z & M4) | (((hq >> 2) & M1) << 4); u.v[3] = (w.w & M4) | (((hq >> 3) & M1) << 4);
+        u.v[4] = ((w.x >> 4) & M4) | (((hq >> 4) & M1) << 4); u.v[5] = ((w.y >> 4) & M4) | (((hq >> 5) & M1) << 4);
+        u.v[6] = ((w.z >> 4) & M4) | (((hq >> 6) & M1) << 4); u.v[7] = ((w.w >> 4) & M4) | (((hq >> 7) & M1) << 4);
+        const uint32_t dm = ld4(chunk + DM + r * 32 + 4 * swzw(r, i));
+        u.a[0] = u.a[1] = half_bits_to_float((uint16_t)(dm & 0xFFFF));
+        u.b[0] = u.b[1] = -half_bits_to_float((uint16_t)(dm >> 16));
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
+// Q2_K : canonical [u8 scales[16] (4-bit sc | 4-bit m << 4)][u8 qs[64]][f16 d][f16 dmin]  (84 B / 256), 16 sub-blocks of 16
+// chunk: Q2 128x64 B (unit = 2 words) | SC 128x16 B (as stored) | DD 128x4 B
+struct FmtQ2K {
+    static constexpr int FAMILY = 10, SUB = 16;
+    static constexpr bool NIB = false;
+    static constexpr bool SIGNED = false;
+    static constexpr bool HAS_MIN = true;
+    static constexpr int Q2 = 0, SC = 128 * 64, DD = SC + 128 * 16;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 84; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 84; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* q2 = chunk + Q2 + r * 64;
+        uint8_t* sc = chunk + SC + r * 16;
+        uint8_t* dd = chunk + DD + r * 4;
+        if (nvalid <= 0) {
+            for (int j = 0; j < 64; j++) q2[j] = 0;
+            for (int j = 0; j < 16; j++) sc[j] = 0;
+            for (int j = 0; j < 4; j++) dd[j] = 0;
+            return;
+        }
+        for (int j = 0; j < 16; j++) sc[j] = src[j];
+        for (int j = 0; j < 4; j++) dd[j] = src[80 + j];
+        const uint8_t* qs = src + 16;
+        for (int i = 0; i < 8; i++) {
+            uint8_t v[32];
+            for (int l = 0; l < 32; l++) {
+                const int e = 32 * i + l, n = e >> 7, j = (e & 127) >> 5, ll = e & 31;
+                v[l] = (qs[32 * n + ll] >> (2 * j)) & 3;
+            }
+            store_2bit_unit(q2 + 8 * swzd(r, i), v);
+        }
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        const uint2 q = ld8<SMEM>(chunk + Q2 + r * 64 + 8 * swzd(r, i));
+        const uint32_t M2 = 0x03030303u;
+        u.v[0] = q.x & M2; u.v[1] = (q.x >> 2) & M2; u.v[2] = (q.x >> 4) & M2; u.v[3] = (q.x >> 6) & M2;
+        u.v[4] = q.y & M2; u.v[5] = (q.y >> 2) & M2; u.v[6] = (q.y >> 4) & M2; u.v[7] = (q.y >> 6) & M2;
+        const uint16_t s2 = ld2(chunk + SC + r * 16 + 2 * i);
+        const uint32_t dd = ld4(chunk + DD + r * 4);
+        const float d = half_bits_to_float((uint16_t)(dd & 0xFFFF)), dmin = half_bits_to_float((uint16_t)(dd >> 16));
+        u.a[0] = __fmul_rn(d, (float)(s2 & 0xF));
+        u.b[0] = __fmul_rn(dmin, (float)((s2 >> 4) & 0xF));
+        u.a[1] = __fmul_rn(d, (float)((s2 >> 8) & 0xF));
+        u.b[1] = __fmul_rn(dmin, (float)(s2 >> 12));
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
+// Q3_K : canonical [u8 hmask[32]][u8 qs[64]][u8 scales[12]][f16 d]  (110 B / 256), 16 sub-blocks of 16,
+//        w = d (sc - 32) (q3 - 4),  q3 = 2 low bits | hmask bit << 2
+// chunk: Q2 128x64 B | HM 128x32 B (hb' words) | SC 128x12 B re-encoded: byte i = lo4(sc[2i]) | lo4(sc[2i+1]) << 4,
+//        byte 8 + i/2 nibble i%2 = hi2(sc[2i]) | hi2(sc[2i+1]) << 2 | D 128x2 B
+struct FmtQ3K {
+    static constexpr int FAMILY = 11, SUB = 16;
+    static constexpr bool NIB = false;
+    static constexpr bool SIGNED = false;
+    static constexpr bool HAS_MIN = false;
+    static constexpr int Q2 = 0, HM = 128 * 64, SC = HM + 128 * 32, D = SC + 128 * 12;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 110; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 110; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* q2 = chunk + Q2 + r * 64;
+        uint8_t* hm = chunk + HM + r * 32;
+        uint8_t* sc = chunk + SC + r * 12;
+        uint8_t* dd = chunk + D + r * 2;
+        if (nvalid <= 0) {
+            for (int j = 0; j < 64; j++) q2[j] = 0;
+            for (int j = 0; j < 32; j++) hm[j] = 0;
+            for (int j = 0; j < 12; j++) sc[j] = 0;
+            dd[0] = dd[1] = 0;
+            return;
+        }
+        const uint8_t* H = src;
+        const uint8_t* qs = src + 32;
+        const uint8_t* s = src + 96;
+        dd[0] = src[108]; dd[1] = src[109];
+        int scl[16];
+        for (int i = 0; i < 16; i++) {
+            const int lo = (i < 8) ? (s[i] & 0xF) : (s[i - 8] >> 4);
+            const int hi = (s[8 + (i % 4)] >> (2 * (i / 4))) & 3;
+            scl[i] = lo | (hi << 4);
+        }
+        for (int i = 0; i < 8; i++) sc[i] = (uint8_t)((scl[2 * i] & 15) | ((scl[2 * i + 1] & 15) << 4));
+        for (int j = 0; j < 4; j++) {
+            const int i0 = 2 * j, i1 = 2 * j + 1;
+            const int n0 = (scl[2 * i0] >> 4) | ((scl[2 * i0 + 1] >> 4) << 2);
+            const int n1 = (scl[2 * i1] >> 4) | ((scl[2 * i1 + 1] >> 4) << 2);
+            sc[8 + j] = (uint8_t)(n0 | (n1 << 4));
+        }
+        for (int i = 0; i < 8; i++) {
+            uint8_t v[32], hb[32];
+            for (int l = 0; l < 32; l++) {
+                const int e = 32 * i + l, n = e >> 7, j = (e & 127) >> 5, ll = e & 31;
+                v[l] = (qs[32 * n + ll] >> (2 * j)) & 3;
+                hb[l] = (H[ll] >> (4 * n + j)) & 1;
+            }
+            store_2bit_unit(q2 + 8 * swzd(r, i), v);
+            store_u32(hm + 4 * swzw(r, i), pack_hibits(hb));
+        }
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        const uint2 q = ld8<SMEM>(chunk + Q2 + r * 64 + 8 * swzd(r, i));
+        const uint32_t hq = ld4(chunk + HM + r * 32 + 4 * swzw(r, i));
+        const uint32_t M2 = 0x03030303u, M1 = 0x01010101u;
+        u.v[0] = (q.x & M2) | (((hq >> 0) & M1) << 2); u.v[1] = ((q.x >> 2) & M2) | (((hq >> 1) & M1) << 2);
+        u.v[2] = ((q.x >> 4) & M2) | (((hq >> 2) & M1) << 2); u.v[3] = ((q.x >> 6) & M2) | (((hq >> 3) & M1) << 2);
+        u.v[4] = (q.y & M2) | (((hq >> 4) & M1) << 2); u.v[5] = ((q.y >> 2) & M2) | (((hq >> 5) & M1) << 2);
+        u.v[6] = ((q.y >> 4) & M2) | (((hq >> 6) & M1) << 2); u.v[7] = ((q.y >> 6) & M2) | (((hq >> 7) & M1) << 2);
+        const uint8_t* sc = chunk + SC + r * 12;
+        const uint32_t b1 = sc[i], b2 = (uint32_t)sc[8 + (i >> 1)] >> (4 * (i & 1));
+        const int s0 = (int)((b1 & 15) | ((b2 & 3) << 4)) - 32;
+        const int s1 = (int)((b1 >> 4) | (((b2 >> 2) & 3) << 4)) - 32;
+        const float d = half_bits_to_float(ld2(chunk + D + r * 2));
+        u.a[0] = __fmul_rn(d, (float)s0);
+        u.a[1] = __fmul_rn(d, (float)s1);
+        u.b[0] = u.b[1] = 0.0f;
+        u.off[0] = u.off[1] = 4;
     }
 };
 

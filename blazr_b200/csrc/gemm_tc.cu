@@ -85,6 +85,11 @@ static cudaError_t gemm_launch_family(int family, const GemmParams& p, int grid,
         case B200Q_FAM_Q4_K: return gemm_launch<B200Q_FAM_Q4_K>(p, grid, smem, st);
         case B200Q_FAM_Q6_K: return gemm_launch<B200Q_FAM_Q6_K>(p, grid, smem, st);
         case B200Q_FAM_Q8_0: return gemm_launch<B200Q_FAM_Q8_0>(p, grid, smem, st);
+        case B200Q_FAM_Q5_K: return gemm_launch<B200Q_FAM_Q5_K>(p, grid, smem, st);
+        case B200Q_FAM_Q4_1: return gemm_launch<B200Q_FAM_Q4_1>(p, grid, smem, st);
+        case B200Q_FAM_Q5_1: return gemm_launch<B200Q_FAM_Q5_1>(p, grid, smem, st);
+        case B200Q_FAM_Q2_K: return gemm_launch<B200Q_FAM_Q2_K>(p, grid, smem, st);
+        case B200Q_FAM_Q3_K: return gemm_launch<B200Q_FAM_Q3_K>(p, grid, smem, st);
         case B200Q_FAM_G4: return gemm_launch<B200Q_FAM_G4>(p, grid, smem, st);
         default: return cudaErrorNotSupported;
     }

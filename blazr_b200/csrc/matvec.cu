@@ -35,6 +35,11 @@ static cudaError_t launch_family(int family, const MatvecParams& p, int mb, int 
         case B200Q_FAM_Q4_K: return mv_launch<B200Q_FAM_Q4_K>(p, mb, grid, smem, st);
         case B200Q_FAM_Q6_K: return mv_launch<B200Q_FAM_Q6_K>(p, mb, grid, smem, st);
         case B200Q_FAM_Q8_0: return mv_launch<B200Q_FAM_Q8_0>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q5_K: return mv_launch<B200Q_FAM_Q5_K>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q4_1: return mv_launch<B200Q_FAM_Q4_1>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q5_1: return mv_launch<B200Q_FAM_Q5_1>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q2_K: return mv_launch<B200Q_FAM_Q2_K>(p, mb, grid, smem, st);
+        case B200Q_FAM_Q3_K: return mv_launch<B200Q_FAM_Q3_K>(p, mb, grid, smem, st);
         case B200Q_FAM_G4: return mv_launch<B200Q_FAM_G4>(p, mb, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }
