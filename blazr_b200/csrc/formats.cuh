@@ -582,6 +582,61 @@ struct FmtQ3K {
     }
 };
 
+// IQ4_XS : canonical [f16 d][u16 scales_h][u8 scales_l[4]][u8 qs[128]]  (136 B / 256), 8 sub-blocks of 32,
+//          w = d (ls - 32) kvalues[q]  with the 16-entry non-linear int8 codebook of IQ4_NL
+// chunk: QS 128x128 B (block ib's 16 bytes as stored) | HDR 128x8 B (as stored)
+// four 4-bit codes (one per byte of x, low nibble) -> four codebook bytes: two PRMTs over the table halves + select
+__device__ __forceinline__ uint32_t iq4_codebook4(uint32_t x) {
+    // kvalues = {-127,-104,-83,-65,-49,-35,-22,-10, 1,13,25,38,53,69,89,113}
+    const uint32_t T0 = 0xBFAD9881u, T1 = 0xF6EADDCFu, T2 = 0x26190D01u, T3 = 0x71594535u;
+    const uint32_t sel = (x & 7u) | ((x >> 4) & 0x70u) | ((x >> 8) & 0x700u) | ((x >> 12) & 0x7000u);
+    const uint32_t lo = __byte_perm(T0, T1, sel), hi = __byte_perm(T2, T3, sel);
+    const uint32_t m = ((x >> 3) & 0x01010101u) * 0xFFu;  // 0xFF in every byte whose code is >= 8
+    return (hi & m) | (lo & ~m);
+}
+struct FmtIQ4XS {
+    static constexpr int FAMILY = 13, SUB = 32;
+    static constexpr bool NIB = false;
+    static constexpr bool SIGNED = true;   // unit bytes are signed int8 codebook values
+    static constexpr bool HAS_MIN = false;
+    static constexpr int QS = 0, HDR = 128 * 128;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 136; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 136; }
+
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t* qs = chunk + QS + r * 128;
+        uint8_t* hdr = chunk + HDR + r * 8;
+        if (nvalid <= 0) {
+            for (int j = 0; j < 128; j++) qs[j] = 0;
+            for (int j = 0; j < 8; j++) hdr[j] = 0;
+            // codes 0 decode to -127: give the padding rows a zero scale (d = 0) so they contribute nothing
+            return;
+        }
+        for (int j = 0; j < 8; j++) hdr[j] = src[j];
+        for (int ib = 0; ib < 8; ib++) {
+            uint8_t* dst = qs + 16 * swz8(r, ib);
+            for (int b = 0; b < 16; b++) dst[b] = src[8 + 16 * ib + b];
+        }
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        uint4 w = ld16<SMEM>(chunk + QS + r * 128 + 16 * swz8(r, i));
+        const uint32_t M4 = 0x0F0F0F0Fu;
+        u.v[0] = iq4_codebook4(w.x & M4); u.v[1] = iq4_codebook4(w.y & M4);
+        u.v[2] = iq4_codebook4(w.z & M4); u.v[3] = iq4_codebook4(w.w & M4);
+        u.v[4] = iq4_codebook4((w.x >> 4) & M4); u.v[5] = iq4_codebook4((w.y >> 4) & M4);
+        u.v[6] = iq4_codebook4((w.z >> 4) & M4); u.v[7] = iq4_codebook4((w.w >> 4) & M4);
+        const uint2 h = ld8<SMEM>(chunk + HDR + r * 8);
+        const float d = half_bits_to_float((uint16_t)(h.x & 0xFFFF));
+        const uint32_t sh = h.x >> 16, sl = h.y;
+        const int ls = (int)(((sl >> (4 * i)) & 0xFu) | (((sh >> (2 * i)) & 3u) << 4)) - 32;
+        u.a[0] = u.a[1] = __fmul_rn(d, (float)ls);
+        u.b[0] = u.b[1] = 0.0f;
+        u.off[0] = u.off[1] = 0;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Source adaptors: 32-element ggml block formats whose arithmetic is exactly expressible in an existing family are
 // re-encoded at upload and then run that family's kernels (no new compute code, dequantized weights and integer

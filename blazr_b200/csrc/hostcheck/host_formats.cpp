@@ -64,6 +64,7 @@ extern "C" int hostfmt_decompose(int ggml_type, const uint8_t* blocks, int64_t N
         case 7: return dump<FmtQ5_1>(blocks, N, K, 1, q, a, b);
         case 10: return dump<FmtQ2K>(blocks, N, K, 1, q, a, b);
         case 11: return dump<FmtQ3K>(blocks, N, K, 1, q, a, b);
+        case 23: return dump<FmtIQ4XS>(blocks, N, K, 1, q, a, b);
         default: return -1;
     }
 }

@@ -21,6 +21,19 @@ inline uint4 lds128(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
 inline uint2 lds64(const void* p) { uint2 v; memcpy(&v, p, 8); return v; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }  // one IEEE rounding, never contracted
 
+// PRMT semantics (selector nibble: bits 0-2 = byte of the 8-byte pool {x, y}, bit 3 = replicate that byte's sign)
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t pool = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t n = (s >> (4 * i)) & 0xF;
+        uint32_t b = (uint32_t)(pool >> (8 * (n & 7))) & 0xFF;
+        if (n & 8) b = (b & 0x80) ? 0xFF : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+
 // exact f16 -> f32 (subnormals, inf, nan included)
 inline float half_bits_to_float(uint16_t h) {
     const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;

@@ -26,6 +26,7 @@ cudaError_t launch_repack_ggml(int family, const uint8_t* src, int64_t src_row_b
         case B200Q_FAM_Q5_1: return repack_launch<B200Q_FAM_Q5_1>(src, src_row_bytes, n0, k0, w, st);
         case B200Q_FAM_Q2_K: return repack_launch<B200Q_FAM_Q2_K>(src, src_row_bytes, n0, k0, w, st);
         case B200Q_FAM_Q3_K: return repack_launch<B200Q_FAM_Q3_K>(src, src_row_bytes, n0, k0, w, st);
+        case B200Q_FAM_IQ4_XS: return repack_launch<B200Q_FAM_IQ4_XS>(src, src_row_bytes, n0, k0, w, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -147,6 +148,7 @@ cudaError_t launch_dequantize(const b200q_weight* w, void* out, int dtype, cudaS
         case B200Q_FAM_Q5_1: return dequant_launch<B200Q_FAM_Q5_1>(w, out, dtype, st);
         case B200Q_FAM_Q2_K: return dequant_launch<B200Q_FAM_Q2_K>(w, out, dtype, st);
         case B200Q_FAM_Q3_K: return dequant_launch<B200Q_FAM_Q3_K>(w, out, dtype, st);
+        case B200Q_FAM_IQ4_XS: return dequant_launch<B200Q_FAM_IQ4_XS>(w, out, dtype, st);
         case B200Q_FAM_G4: return dequant_launch<B200Q_FAM_G4>(w, out, dtype, st);
         default: return cudaErrorInvalidValue;
     }
@@ -230,6 +232,7 @@ cudaError_t launch_int_partials(const b200q_weight* w, const uint8_t* xq, int64_
         case B200Q_FAM_Q5_1: return partials_launch<B200Q_FAM_Q5_1>(w, xq, M, out, st);
         case B200Q_FAM_Q2_K: return partials_launch<B200Q_FAM_Q2_K>(w, xq, M, out, st);
         case B200Q_FAM_Q3_K: return partials_launch<B200Q_FAM_Q3_K>(w, xq, M, out, st);
+        case B200Q_FAM_IQ4_XS: return partials_launch<B200Q_FAM_IQ4_XS>(w, xq, M, out, st);
         case B200Q_FAM_G4: return partials_launch<B200Q_FAM_G4>(w, xq, M, out, st);
         default: return cudaErrorInvalidValue;
     }

@@ -27,7 +27,7 @@ def hostlib():
     return C.CDLL(so)
 
 
-NATIVE = ["Q4_K", "Q6_K", "Q8_0", "Q5_K", "Q4_1", "Q5_1", "Q2_K", "Q3_K"]
+NATIVE = ["Q4_K", "Q6_K", "Q8_0", "Q5_K", "Q4_1", "Q5_1", "Q2_K", "Q3_K", "IQ4_XS"]
 ADAPTED = ["Q4_0", "Q5_0", "IQ4_NL"]
 
 
