@@ -291,7 +291,10 @@ def run_b200(args):
 
     extra = {}
     if not args.no_extra and rank == 0 and world == 1:
-        extra = extras(client, cfg, scheme, pk)
+        try:
+            extra = extras(client, cfg, scheme, pk)
+        except Exception as ex:  # secondary measurements must never take the headline line down
+            extra = {"error": repr(ex)[:300]}
 
     if rank == 0:
         toks = M * args.steps / (ms * 1e-3)
@@ -385,6 +388,39 @@ def extras(client, cfg, scheme, pk):
         del decb
     except Exception as ex:  # secondary number: never take the headline down with it
         out["decode_batch32_step"] = {"error": repr(ex)[:200]}
+    # MoE decode (BASELINE config 5 shapes: DeepSeek-V2-Lite, 64 routed experts + 2 shared halves, top-6; gate|up Q4_K
+    # [2816 x 2048], down Q8_0 [2048 x 1408] because K = 1408 is not a multiple of 256): one token through the expert MLP =
+    # grouped gate|up matvec over 8 slots, SwiGLU+quantise, grouped down matvec (3 launches), routing rotated every call
+    try:
+        E, top_k, hidden, ffn = 66, 8, 2048, 1408
+        tg, td = synth.GGML["Q4_K"], synth.GGML["Q8_0"]
+        gu = [client.weight_from_ggml(tg, decode.random_ggml_device("Q4_K", 2 * ffn, hidden, 500 + e, client.device), 2 * ffn, hidden) for e in range(E)]
+        dn = [client.weight_from_ggml(td, decode.random_ggml_device("Q8_0", hidden, ffn, 700 + e, client.device), hidden, ffn) for e in range(E)]
+        moe = ops.MoeMlp(client, [ops.ExpertWeights(g, d) for g, d in zip(gu, dn)], ffn, hidden)
+        x = torch.randn((1, hidden), device=client.device)
+        gen = torch.Generator(device="cpu"); gen.manual_seed(3)
+        nsel = 16
+        sels = [torch.cat([torch.randperm(64, generator=gen)[:6], torch.tensor([64, 65])]).to(torch.int32).reshape(1, top_k).to(client.device) for _ in range(nsel)]
+        gw = torch.full((1, top_k), 1.0 / top_k, device=client.device)
+        for sl in sels:
+            moe.forward_decode(x, sl, gw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            for sl in sels:
+                moe.forward_decode(x, sl, gw)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * nsel)
+        wbytes = top_k * (gu[0].canonical_bytes + dn[0].canonical_bytes)
+        out["moe_decode_layer"] = {"us": us, "GBs": wbytes / (us * 1e-6) / 1e9, "frac_hbm": wbytes / (us * 1e-6) / 1e9 / pk["hbm_gbs"],
+                                   "weight_bytes_per_token": wbytes,
+                                   "what": "DeepSeek-V2-Lite expert MLP, 1 token: 6 routed of 64 + 2 shared halves, Q4_K gate|up + Q8_0 down, eager launches "
+                                           "(quantise, grouped gate|up, SwiGLU, grouped down, torch combine)"}
+    except Exception as ex:
+        out["moe_decode_layer"] = {"error": repr(ex)[:200]}
     return out
 
 
