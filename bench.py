@@ -98,7 +98,7 @@ def cpu_tokens_per_s(model: str, scheme: str, batch: int, budget_s: float = 12.0
     qd, kvd = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
     shapes = dict(q=(qd, cfg.hidden), k=(kvd, cfg.hidden), v=(kvd, cfg.hidden), o=(cfg.hidden, qd), gate=(cfg.ffn, cfg.hidden),
                   up=(cfg.ffn, cfg.hidden), down=(cfg.hidden, cfg.ffn))
-    ggml_like = {p: (f if f in synth.GGML else "Q4_0") for p, f in fm.items()}  # INT4 group formats: timed as a 4-bit block format
+    ggml_like = {p: (f if f in synth.GGML else "Q4_K") for p, f in fm.items()}  # INT4 group formats: timed as the 4-bit block format with a tuned kernel
     lin = []
     for p, (N, K) in shapes.items():
         t = synth.GGML[ggml_like[p]]
@@ -107,19 +107,19 @@ def cpu_tokens_per_s(model: str, scheme: str, batch: int, budget_s: float = 12.0
     params_layer = sum(N * K for _, N, K, _ in lin)
     # warm-up + timed repetitions of one layer
     for t, N, K, blk in lin[:2]:
-        oracle.matvec_ggml_q8(t, blk, N, K, *xs[K])
+        oracle.matvec_ggml_q8_fast(t, blk, N, K, *xs[K])
     reps, t0 = 0, time.perf_counter()
     while True:
         for t, N, K, blk in lin:
-            oracle.matvec_ggml_q8(t, blk, N, K, *xs[K])
+            oracle.matvec_ggml_q8_fast(t, blk, N, K, *xs[K])
         reps += 1
         if time.perf_counter() - t0 > budget_s:
             break
     t_layer = (time.perf_counter() - t0) / reps
     params_total = params_layer * cfg.n_layers + cfg.vocab * cfg.hidden
     t_token = t_layer * params_total / params_layer
-    sample = (f"{reps} x one layer ({params_layer / 1e6:.0f}M weights, 7 projections, M={batch}) of {model} {scheme} through the oracle's "
-              f"packed-block int8 matvec, OpenMP over rows; scaled by weights to 7L+1 projections")
+    sample = (f"{reps} x one layer ({params_layer / 1e6:.0f}M weights, 7 projections, M={batch}) of {model} {scheme} through the CPU port's "
+              f"AVX2 packed-block int8 matvec (oracle/cpu_fast.c), OpenMP over rows; scaled by weights to 7L+1 projections")
     return batch / t_token, cores, sample
 
 

@@ -158,6 +158,16 @@ def matvec_ggml_q8(t: int, blocks: np.ndarray, N: int, K: int, xq, xd, xbs) -> n
     return Y
 
 
+def matvec_ggml_q8_fast(t: int, blocks: np.ndarray, N: int, K: int, xq, xd, xbs) -> np.ndarray:
+    """the TIMED CPU baseline (cpu_fast.c): AVX2 + OpenMP packed-block kernels for Q8_0 / Q4_K / Q6_K, generic port otherwise"""
+    M = xq.shape[0]
+    Y = np.empty((M, N), dtype=np.float32)
+    rc = lib().orc_matvec_fast(C.c_int(t), _p(blocks), C.c_int64(N), C.c_int64(K), _p(xq), _p(xd), _p(xbs), C.c_int64(M), _p(Y))
+    if rc != 0:
+        return matvec_ggml_q8(t, blocks, N, K, xq, xd, xbs)
+    return Y
+
+
 # ------------------------------------------------------------------------------------------------
 # AWQ / GPTQ
 # ------------------------------------------------------------------------------------------------

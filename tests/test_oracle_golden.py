@@ -134,3 +134,26 @@ def test_shard_range_reference_rule():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+@pytest.mark.parametrize("name", ["Q8_0", "Q4_K", "Q6_K"])
+@pytest.mark.parametrize("M", [1, 3])
+def test_timed_cpu_baseline_matches_exact_oracle(name, M):
+    """oracle/cpu_fast.c (the AVX2 kernels bench.py times as the CPU baseline) computes the same int8-activation matvec as
+    the exact-accumulation oracle, to f32 accumulation accuracy"""
+    from blazr_b200 import synth
+    t = synth.GGML[name]
+    N, K = 300, 1024
+    blk = synth.random_ggml(t, N, K, seed=4)
+    x = synth.random_act(M, K, seed=5)
+    xq, xd, xbs = oracle.quantize_act(x)
+    y = oracle.matvec_ggml_q8_fast(t, blk, N, K, xq, xd, xbs)
+    qi, a, b, sub = oracle.decompose_ggml(t, blk, N, K)
+    ref = oracle.matmul_q8(qi, a, b, sub, x)
+    assert float(np.abs(y - ref).max() / np.abs(ref).max()) < 1e-5
+    # a type without a fast kernel falls back to the generic port
+    t2 = synth.GGML["Q5_K"]
+    blk2 = synth.random_ggml(t2, 64, 512, seed=6)
+    x2 = synth.random_act(1, 512, seed=7)
+    q2 = oracle.quantize_act(x2)
+    assert np.array_equal(oracle.matvec_ggml_q8_fast(t2, blk2, 64, 512, *q2), oracle.matvec_ggml_q8(t2, blk2, 64, 512, *q2))
