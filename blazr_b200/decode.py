@@ -245,6 +245,10 @@ class Decoder:
         self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0" and not self.wide  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
+        # EXPERIMENTAL (B200Q_DSTEP=1, single GPU, M <= 4): persistent op-list kernel, 3 launches per layer instead of 8
+        self.programs = None
+        if _os.environ.get("B200Q_DSTEP", "0") != "0" and tp_world == 1 and not self.wide and not self.fused:
+            self._build_programs()
         # tensor parallel: one-shot NVLink all-reduce of the f64 partial sums (csrc/comm.cu); B200Q_TP_NCCL=1 falls back
         # to torch.distributed (NCCL) all-reduce of f32 partials for comparison
         self.comm = None
@@ -315,6 +319,51 @@ class Decoder:
             return self.c.weight_from_decomposed(dq)
         raise ValueError(fmt)
 
+    def _build_programs(self):
+        """op lists between the attention operators of a step (same buffers and order as step())"""
+        cfg, M = self.cfg, self.M
+        progs = []
+        hin, hout = self.h, self.h2
+        delta = None
+        for lay in self.layers:
+            p1 = ops.Program(self.dev)
+            p1.normq(hin, delta, hout, lay["attn_norm"], cfg.eps, self.xq_h)
+            hin, hout = hout, hin
+            for ln in lay["qkv"]:
+                p1.matvec(ln.w, self.xq_h, M, self.qkv, ln.col0, ln.ws)
+            p2 = ops.Program(self.dev)
+            for ln in lay["o"]:
+                p2.matvec(ln.w, self.xq_attn, M, self.delta, ln.col0, ln.ws)
+            p2.normq(hin, self.delta, hout, lay["mlp_norm"], cfg.eps, self.xq_h)
+            hin, hout = hout, hin
+            for ln in lay["gu"]:
+                p2.matvec(ln.w, self.xq_h, M, self.gu, ln.col0, ln.ws)
+            p2.swigluq(self.gu, self.ff, M, self.xq_ff)
+            for ln in lay["down"]:
+                p2.matvec(ln.w, self.xq_ff, M, self.delta2, ln.col0, ln.ws)
+            delta = self.delta2
+            progs.append((p1.finalize(), p2.finalize()))
+        pf = ops.Program(self.dev)
+        pf.normq(hin, delta, hout, self.final_norm, cfg.eps, self.xq_h)
+        for ln in self.head:
+            pf.matvec(ln.w, self.xq_h, M, self.logits_local, ln.col0, ln.ws)
+        self.programs = (progs, pf.finalize())
+
+    def _step_programs(self):
+        L, cfg, M = ops.lib(), self.cfg, self.M
+        st = ops._stream_ptr(self.dev)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        ops._check(L.b200q_embed(P(self.embed), P(self.ids), C.c_int64(cfg.hidden), C.c_int64(M), P(self.h), st))
+        progs, pf = self.programs
+        for lay, (p1, p2) in zip(self.layers, progs):
+            p1.launch()
+            ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
+                                           C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
+                                           P(self.xq_attn), None, st))
+            p2.launch()
+        pf.launch()
+        ops._check(L.b200q_argmax(P(self.logits), C.c_int64(self.logits.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
+
     # ---- one decode step ------------------------------------------------------------------------------
     def _prefetch(self, lins: List[_Linear]):
         """L2 prefetch hint for the matvec that follows the upcoming glue operator"""
@@ -355,6 +404,8 @@ class Decoder:
 
     def step(self):
         """ids (device) -> next ids (device); positions advance on the device: graph-replayable."""
+        if self.programs is not None:
+            return self._step_programs()
         L, cfg, M = ops.lib(), self.cfg, self.M
         st = ops._stream_ptr(self.dev)
         P = lambda t: C.c_void_p(t.data_ptr())
