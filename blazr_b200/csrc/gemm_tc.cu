@@ -1,5 +1,7 @@
 // gemm_tc.cu -- host side of the tcgen05 dequant-GEMM: activation staging, split-K reduction, tile plan, dispatch.
 // The kernel lives in gemm_impl.cuh and is instantiated per format in inst_<format>.cu.
+#include <cstdlib>
+
 #include "gemm_impl.cuh"
 
 namespace b200q {
@@ -135,10 +137,15 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     if (nx > GT_NX) nx = GT_NX;
     if (nx < 4) nx = 4;
     if (p.xsub == 4) nx = Mt <= 32 ? 4 : 3;  // whole-chunk stages: keep the shared memory for the weight ring (the HBM stream)
+    int nw_cap = GT_MAX_NW;
+    // tuning knobs (defaults unchanged): B200Q_GEMM_NX / B200Q_GEMM_NW trade weight stages for activation stages
+    if (const char* e = getenv("B200Q_GEMM_NX")) { int v = atoi(e); if (v >= 2 && v <= GT_NX) nx = v; }
+    if (const char* e = getenv("B200Q_GEMM_NW")) { int v = atoi(e); if (v >= 2 && v <= GT_MAX_NW) nw_cap = v; }
+    if (GT_HDR + nx * p.x_stage_bytes + 2 * p.w_stage_bytes > 227 * 1024) return cudaErrorNotSupported;
     p.nx = nx;
     int avail = 227 * 1024 - GT_HDR - nx * p.x_stage_bytes;
     int nw = avail / p.w_stage_bytes;
-    if (nw > GT_MAX_NW) nw = GT_MAX_NW;
+    if (nw > nw_cap) nw = nw_cap;
     if (nw < 2) return cudaErrorNotSupported;
     p.nw = nw;
     p.nslots = Mt > 64 ? 2 : 3;   // TMEM: 2 accumulators x Mt (Mt <= 128) or one of 256 columns, A slots of 128 columns on top
