@@ -94,6 +94,12 @@ def cpu_tokens_per_s(model: str, scheme: str, batch: int, budget_s: float = 12.0
 
     cfg = decode.PRESETS[model]
     cores = os.cpu_count() or 1
+    try:  # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core regardless
+        import ctypes
+        oracle.lib()
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+    except Exception:
+        pass
     fm = decode.layer_formats(cfg, scheme, cfg.n_layers // 2)
     qd, kvd = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
     shapes = dict(q=(qd, cfg.hidden), k=(kvd, cfg.hidden), v=(kvd, cfg.hidden), o=(cfg.hidden, qd), gate=(cfg.ffn, cfg.hidden),
