@@ -14,6 +14,7 @@ struct b200q_program {
     StepOp* ops_dev;
     unsigned int* bar_dev;  // [0] arrivals, [32] generation (separate 128-byte lines)
     int nstages, stage_bytes, xhat_bytes, smem_bytes;
+    std::vector<void*> owned;  // device scratch owned by the program (argmax candidates)
 };
 
 template <int MB>
@@ -114,6 +115,62 @@ int32_t b200q_program_add_matvec(b200q_program* p, const b200q_weight* w, const 
     return B200Q_OK;
 }
 
+int32_t b200q_program_add_attn(b200q_program* p, const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table,
+                               int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq_out) {
+    if (!p || p->finalized || !qkv || !pos || !cache_k || !cache_v || !rope_table || !xq_out || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads ||
+        max_ctx <= 0)
+        return B200Q_ERR_INVALID_ARG;
+    if (head_dim != 64 && head_dim != 128) return B200Q_ERR_UNSUPPORTED;
+    if (((int64_t)n_heads * head_dim) % CHUNK_K) return B200Q_ERR_INVALID_ARG;
+    int32_t rc = set_m(p, M);
+    if (rc) return rc;
+    StepOp op;
+    memset(&op, 0, sizeof(op));
+    op.type = DS_ATTN;
+    op.M = (int)M; op.qkv = qkv; op.pos = pos; op.cache_k = cache_k; op.cache_v = cache_v; op.rope = rope_table;
+    op.nh = n_heads; op.nkv = n_kv_heads; op.hd = head_dim; op.max_ctx = max_ctx; op.xq_out = (uint8_t*)xq_out;
+    p->ops.push_back(op);
+    return B200Q_OK;
+}
+
+/* greedy sampling inside the program: two ops (per-CTA candidates, then the final pick by CTA 0) */
+int32_t b200q_program_add_argmax(b200q_program* p, const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc) {
+    if (!p || p->finalized || !logits || !out_ids || V <= 0) return B200Q_ERR_INVALID_ARG;
+    int32_t rc = set_m(p, M);
+    if (rc) return rc;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(p->device);
+    float* cv = nullptr;
+    int* ci = nullptr;
+    cudaError_t e = cudaMalloc(&cv, sizeof(float) * (size_t)M * p->num_sms);
+    if (e == cudaSuccess) e = cudaMalloc(&ci, sizeof(int) * (size_t)M * p->num_sms);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return B200Q_ERR_CUDA;
+    p->owned.push_back(cv);
+    p->owned.push_back(ci);
+    StepOp op;
+    memset(&op, 0, sizeof(op));
+    op.type = DS_ARGMAX_A;
+    op.M = (int)M; op.V = (int)V; op.logits = logits; op.cand_val = cv; op.cand_idx = ci; op.ids = out_ids; op.pos_inc = pos_inc;
+    p->ops.push_back(op);
+    op.type = DS_ARGMAX_B;
+    p->ops.push_back(op);
+    return B200Q_OK;
+}
+
+int32_t b200q_program_add_embed(b200q_program* p, const void* table_f16, const int64_t* ids, int64_t H, int64_t M, float* h) {
+    if (!p || p->finalized || !table_f16 || !ids || !h || H <= 0) return B200Q_ERR_INVALID_ARG;
+    int32_t rc = set_m(p, M);
+    if (rc) return rc;
+    StepOp op;
+    memset(&op, 0, sizeof(op));
+    op.type = DS_EMBED;
+    op.M = (int)M; op.H = (int)H; op.table = (const __half*)table_f16; op.ids = const_cast<int64_t*>(ids); op.h_out = h;
+    p->ops.push_back(op);
+    return B200Q_OK;
+}
+
 int32_t b200q_program_finalize(b200q_program* p) {
     if (!p || p->finalized || p->ops.empty()) return B200Q_ERR_INVALID_ARG;
     int max_chunk = 0;
@@ -123,6 +180,12 @@ int32_t b200q_program_finalize(b200q_program* p) {
             if (op.chunk_bytes > max_chunk) max_chunk = op.chunk_bytes;
             const size_t x = (size_t)op.KC * op.M * ACT_REC_BYTES;
             if (x > max_x) max_x = x;
+        } else if (op.type == DS_ATTN) {
+            // s_o [512 / (hd/4)][hd] f64 + 16 f64 + 16 f32 + 3 hd f32 + max_ctx f32 (dstep_impl.cuh ds_attention)
+            const size_t x = (size_t)(DS_CONSUMERS / (op.hd / 4)) * op.hd * 8 + 128 + 64 + 3 * (size_t)op.hd * 4 + (size_t)op.max_ctx * 4;
+            if (x > max_x) max_x = x;
+        } else if (op.type == DS_ARGMAX_A) {
+            if (max_x < 256) max_x = 256;
         }
     p->stage_bytes = max_chunk > 0 ? ((max_chunk + 127) & ~127) : 128;
     p->xhat_bytes = (int)((max_x + 127) & ~(size_t)127);
@@ -168,6 +231,7 @@ int32_t b200q_program_free(b200q_program* p) {
     if (!p) return B200Q_OK;
     if (p->ops_dev) cudaFree(p->ops_dev);
     if (p->bar_dev) cudaFree(p->bar_dev);
+    for (void* q : p->owned) cudaFree(q);
     delete p;
     return B200Q_OK;
 }

@@ -13,7 +13,7 @@
 
 namespace b200q {
 
-enum { DS_END = 0, DS_NORMQ = 1, DS_MATVEC = 2, DS_SWIGLUQ = 3 };
+enum { DS_END = 0, DS_NORMQ = 1, DS_MATVEC = 2, DS_SWIGLUQ = 3, DS_ATTN = 4, DS_ARGMAX_A = 5, DS_ARGMAX_B = 6, DS_EMBED = 7 };
 
 struct StepOp {
     int type, family, gpc, chunk_bytes;
@@ -30,9 +30,24 @@ struct StepOp {
     float* h_out;
     const float* norm_w;
     const float* gate_up;     // SWIGLUQ
-    uint8_t* xq_out;          // NORMQ / SWIGLUQ output records
+    uint8_t* xq_out;          // NORMQ / SWIGLUQ / ATTN output records
     float eps;
     int pad1;
+    // ATTN: qkv [M, (nh + 2 nkv) hd], cache [M][max_ctx][nkv][hd], rope [max_ctx][hd/2][2], pos [M]
+    const float* qkv;
+    const int* pos;
+    float* cache_k;
+    float* cache_v;
+    const float* rope;
+    int nh, nkv, hd, max_ctx;
+    // ARGMAX_A / ARGMAX_B: logits [M, V] -> candidates [M][G] -> ids [M], pos[m]++ ; EMBED: h_out[m, :] = table[ids[m], :]
+    const float* logits;
+    float* cand_val;
+    int* cand_idx;
+    int64_t* ids;
+    int* pos_inc;
+    const __half* table;
+    int V, pad2;
 };
 
 struct StepParams {
@@ -264,6 +279,134 @@ __device__ __forceinline__ void ds_fixup(const StepOp& op, const SkPlan& sp, int
     }
 }
 
+// ---- ATTN op: port of decode_ops.cu attn_decode_kernel<HD> to the 512 consumer threads of one CTA (named barrier 4,
+// scratch carved from the record region, qkv read through L2).  Same operation order => same bits. ----
+template <int HD>
+__device__ __forceinline__ void ds_attention(const StepOp& op, int head, int m, uint8_t* scratch, int t) {
+    const int warp = t >> 5, lane = t & 31;
+    constexpr int NT = DS_CONSUMERS, NW = NT / 32;
+    constexpr int QE = HD / 4, EG = HD / 4, JG = NT / EG;
+    double* s_o = reinterpret_cast<double*>(scratch);                  // [JG][HD]
+    double* s_redd = s_o + JG * HD;                                      // [NW]
+    float* s_redf = reinterpret_cast<float*>(s_redd + NW);               // [NW]
+    float* sq = s_redf + NW;                                             // [HD] x 3, 16-byte aligned (NW = 16)
+    float* sk = sq + HD;
+    float* sv = sk + HD;
+    float* s_sc = sv + HD;                                               // [max_ctx]
+    const int nh = op.nh, nkv = op.nkv, max_ctx = op.max_ctx, M = op.M;
+    const int kvh = head / (nh / nkv);
+    const int p = op.pos[m];
+    const int row = (nh + 2 * nkv) * HD;
+    const float* qsrc = op.qkv + (size_t)m * row + (size_t)head * HD;
+    const float* ksrc = op.qkv + (size_t)m * row + (size_t)(nh + kvh) * HD;
+    const float* vsrc = op.qkv + (size_t)m * row + (size_t)(nh + nkv + kvh) * HD;
+    float* ck = op.cache_k + ((size_t)m * max_ctx) * nkv * HD + (size_t)kvh * HD;
+    float* cv = op.cache_v + ((size_t)m * max_ctx) * nkv * HD + (size_t)kvh * HD;
+    const size_t pstride = (size_t)nkv * HD;
+    const float* rt = op.rope + (size_t)p * HD;
+    if (t < HD / 2) {
+        const float c = rt[2 * t], sn = rt[2 * t + 1];
+        const float q0 = __ldcg(qsrc + 2 * t), q1 = __ldcg(qsrc + 2 * t + 1);
+        sq[2 * t] = __fsub_rn(__fmul_rn(q0, c), __fmul_rn(q1, sn));
+        sq[2 * t + 1] = __fadd_rn(__fmul_rn(q0, sn), __fmul_rn(q1, c));
+        const float k0 = __ldcg(ksrc + 2 * t), k1 = __ldcg(ksrc + 2 * t + 1);
+        const float r0 = __fsub_rn(__fmul_rn(k0, c), __fmul_rn(k1, sn)), r1 = __fadd_rn(__fmul_rn(k0, sn), __fmul_rn(k1, c));
+        sk[2 * t] = r0; sk[2 * t + 1] = r1;
+        const float v0 = __ldcg(vsrc + 2 * t), v1 = __ldcg(vsrc + 2 * t + 1);
+        sv[2 * t] = v0; sv[2 * t + 1] = v1;
+        if (head % (nh / nkv) == 0) {
+            ck[(size_t)p * pstride + 2 * t] = r0; ck[(size_t)p * pstride + 2 * t + 1] = r1;
+            cv[(size_t)p * pstride + 2 * t] = v0; cv[(size_t)p * pstride + 2 * t + 1] = v1;
+        }
+    }
+    named_bar_sync(4, NT);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
+    float lmax = -INFINITY;
+    {
+        const int part = t & 3;
+        for (int j0 = 0; j0 <= p; j0 += NT / 4) {
+            const int j = j0 + (t >> 2);
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            if (j <= p) {
+                const float* kr = (j < p) ? ck + (size_t)j * pstride + part * QE : sk + part * QE;
+                const float* qq = sq + part * QE;
+#pragma unroll
+                for (int e = 0; e < QE; e += 4) {
+                    const float4 kk = *reinterpret_cast<const float4*>(kr + e);
+                    d0 = fma((double)qq[e + 0], (double)kk.x, d0); d1 = fma((double)qq[e + 1], (double)kk.y, d1);
+                    d2 = fma((double)qq[e + 2], (double)kk.z, d2); d3 = fma((double)qq[e + 3], (double)kk.w, d3);
+                }
+            }
+            double d = (d0 + d1) + (d2 + d3);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (j <= p) {
+                const float sc = __fmul_rn((float)d, scale);
+                if (part == 0) s_sc[j] = sc;
+                lmax = fmaxf(lmax, sc);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+    if (lane == 0) s_redf[warp] = lmax;
+    named_bar_sync(4, NT);
+    float gmax = s_redf[0];
+#pragma unroll
+    for (int i = 1; i < NW; i++) gmax = fmaxf(gmax, s_redf[i]);
+    double lsum = 0.0;
+    for (int j = t; j <= p; j += NT) {
+        const float pj = det_expf(__fsub_rn(s_sc[j], gmax));
+        s_sc[j] = pj;
+        lsum += (double)pj;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if (lane == 0) s_redd[warp] = lsum;
+    named_bar_sync(4, NT);
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) dsum += s_redd[i];
+    const float den = (float)dsum;
+    {
+        const int eg = t % EG, jg = t / EG;
+        double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+        for (int j = jg; j <= p; j += JG) {
+            const float pj = s_sc[j];
+            const float4 vv = (j < p) ? *reinterpret_cast<const float4*>(cv + (size_t)j * pstride + 4 * eg) : *reinterpret_cast<const float4*>(sv + 4 * eg);
+            o0 = fma((double)pj, (double)vv.x, o0); o1 = fma((double)pj, (double)vv.y, o1);
+            o2 = fma((double)pj, (double)vv.z, o2); o3 = fma((double)pj, (double)vv.w, o3);
+        }
+        s_o[jg * HD + 4 * eg + 0] = o0; s_o[jg * HD + 4 * eg + 1] = o1; s_o[jg * HD + 4 * eg + 2] = o2; s_o[jg * HD + 4 * eg + 3] = o3;
+        named_bar_sync(4, NT);
+    }
+    if (t < HD) {
+        double o = 0.0;
+#pragma unroll
+        for (int i = 0; i < JG; i++) o += s_o[i * HD + t];
+        const float outv = __fdiv_rn((float)o, den);
+        const int kglob = head * HD + t;
+        const int kc = kglob / CHUNK_K, tin = kglob % CHUNK_K;
+        uint8_t* rec = op.xq_out + ((size_t)kc * M + m) * ACT_REC_BYTES;
+        float amax = fabsf(outv);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        const float d = __fdiv_rn(amax, 127.0f);
+        const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+        const int q = (int)roundf(__fmul_rn(outv, id));
+        int s = q;
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const int s_hi = __shfl_sync(0xffffffffu, s, 16);
+        rec[tin] = (uint8_t)(int8_t)q;
+        if (lane == 0) {
+            reinterpret_cast<float*>(rec + 256)[tin >> 5] = d;
+            reinterpret_cast<uint32_t*>(rec + 288)[tin >> 5] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
+        }
+    }
+    named_bar_sync(4, NT);   // the scratch is reused by the next (head, m) of this CTA
+}
+
 template <int MB>
 __device__ __forceinline__ void ds_consume_family(const StepOp& op, const StepParams& p, const SkPlan& sp, int n_chunks, int64_t g, uint8_t* stages,
                                                   const uint8_t* xhat, uint64_t* full, uint64_t* empty, int& s, uint32_t& ph, int tid, int warp, int lane) {
@@ -415,6 +558,62 @@ __global__ void __launch_bounds__(MV_THREADS, 1) dstep_kernel(const StepParams p
                         ds_quant_store_record(v, op.xq_out + ((size_t)kc * op.M + m) * ACT_REC_BYTES, tid);
                     }
                 }
+            }
+        }
+        else if (!is_fix && op.type == DS_ATTN) {
+            for (int hm = (int)g; hm < op.nh * op.M; hm += (int)G) {
+                const int head = hm % op.nh, m = hm / op.nh;
+                if (op.hd == 128) ds_attention<128>(op, head, m, xhat, tid);
+                else ds_attention<64>(op, head, m, xhat, tid);
+            }
+        } else if (!is_fix && op.type == DS_ARGMAX_A) {
+            // candidates of this CTA's slice of the vocabulary (lowest index wins ties, as argmax_kernel)
+            const int V = op.V;
+            const int lo = (int)((int64_t)g * V / G), hi = (int)((int64_t)(g + 1) * V / G);
+            float* sv_ = reinterpret_cast<float*>(xhat);
+            int* si_ = reinterpret_cast<int*>(xhat + 64);
+            for (int m = 0; m < op.M; m++) {
+                const float* rowp = op.logits + (size_t)m * V;
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int i = lo + tid; i < hi; i += DS_CONSUMERS) {
+                    const float v = __ldcg(rowp + i);
+                    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                if (lane == 0) { sv_[warp] = best; si_[warp] = bi; }
+                named_bar_sync(4, DS_CONSUMERS);
+                if (tid == 0) {
+                    for (int w_ = 1; w_ < MV_CONSUMER_WARPS; w_++)
+                        if (sv_[w_] > best || (sv_[w_] == best && si_[w_] < bi)) { best = sv_[w_]; bi = si_[w_]; }
+                    op.cand_val[(size_t)m * G + g] = best;
+                    op.cand_idx[(size_t)m * G + g] = bi;
+                }
+                named_bar_sync(4, DS_CONSUMERS);
+            }
+        } else if (!is_fix && op.type == DS_ARGMAX_B) {
+            if (g == 0 && tid < op.M) {
+                const int m = tid;
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int c = 0; c < (int)G; c++) {
+                    const float v = __ldcg(op.cand_val + (size_t)m * G + c);
+                    const int i = __ldcg(op.cand_idx + (size_t)m * G + c);
+                    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+                }
+                op.ids[m] = bi;
+                if (op.pos_inc) op.pos_inc[m] += 1;
+            }
+        } else if (!is_fix && op.type == DS_EMBED) {
+            const int H = op.H;
+            for (int idx = (int)g * DS_CONSUMERS + tid; idx < op.M * H; idx += (int)G * DS_CONSUMERS) {
+                const int m = idx / H, kk = idx % H;
+                op.h_out[(size_t)m * H + kk] = __half2float(op.table[(size_t)op.ids[m] * H + kk]);
             }
         }
         // ---- end of op: every CTA's outputs (consumer stores + fix-up stores) are complete before anyone starts the next ----

@@ -247,8 +247,12 @@ class Decoder:
         self.graph = None
         # EXPERIMENTAL (B200Q_DSTEP=1, single GPU, M <= 4): persistent op-list kernel, 3 launches per layer instead of 8
         self.programs = None
+        self.step_program = None
         if _os.environ.get("B200Q_DSTEP", "0") != "0" and tp_world == 1 and not self.wide and not self.fused:
-            self._build_programs()
+            if _os.environ.get("B200Q_DSTEP") == "2":
+                self._build_step_program()
+            else:
+                self._build_programs()
         # tensor parallel: one-shot NVLink all-reduce of the f64 partial sums (csrc/comm.cu); B200Q_TP_NCCL=1 falls back
         # to torch.distributed (NCCL) all-reduce of f32 partials for comparison
         self.comm = None
@@ -318,6 +322,35 @@ class Decoder:
                                            ops.DecomposedQuantMethod("gptq", gs), (nrows, k1 - k0))
             return self.c.weight_from_decomposed(dq)
         raise ValueError(fmt)
+
+    def _build_step_program(self):
+        """B200Q_DSTEP=2: the WHOLE step as one program / one launch (embed ... argmax), attention included"""
+        cfg, M = self.cfg, self.M
+        pr = ops.Program(self.dev)
+        pr.embed(self.embed, self.ids, self.h)
+        hin, hout = self.h, self.h2
+        delta = None
+        for lay in self.layers:
+            pr.normq(hin, delta, hout, lay["attn_norm"], cfg.eps, self.xq_h)
+            hin, hout = hout, hin
+            for ln in lay["qkv"]:
+                pr.matvec(ln.w, self.xq_h, M, self.qkv, ln.col0, ln.ws)
+            pr.attn(self.qkv, self.pos, lay["ck"], lay["cv"], self.rope, self.nh, self.nkv, cfg.head_dim, self.max_ctx, M, self.xq_attn)
+            for ln in lay["o"]:
+                pr.matvec(ln.w, self.xq_attn, M, self.delta, ln.col0, ln.ws)
+            pr.normq(hin, self.delta, hout, lay["mlp_norm"], cfg.eps, self.xq_h)
+            hin, hout = hout, hin
+            for ln in lay["gu"]:
+                pr.matvec(ln.w, self.xq_h, M, self.gu, ln.col0, ln.ws)
+            pr.swigluq(self.gu, self.ff, M, self.xq_ff)
+            for ln in lay["down"]:
+                pr.matvec(ln.w, self.xq_ff, M, self.delta2, ln.col0, ln.ws)
+            delta = self.delta2
+        pr.normq(hin, delta, hout, self.final_norm, cfg.eps, self.xq_h)
+        for ln in self.head:
+            pr.matvec(ln.w, self.xq_h, M, self.logits_local, ln.col0, ln.ws)
+        pr.argmax(self.logits, self.ids, self.pos)
+        self.step_program = pr.finalize()
 
     def _build_programs(self):
         """op lists between the attention operators of a step (same buffers and order as step())"""
@@ -404,6 +437,8 @@ class Decoder:
 
     def step(self):
         """ids (device) -> next ids (device); positions advance on the device: graph-replayable."""
+        if self.step_program is not None:
+            return self.step_program.launch()
         if self.programs is not None:
             return self._step_programs()
         L, cfg, M = ops.lib(), self.cfg, self.M

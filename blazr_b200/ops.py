@@ -55,7 +55,7 @@ EXPORTS = [
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
     "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
-    "b200q_swiglu_f32", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq",
+    "b200q_swiglu_f32", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq", "b200q_program_add_attn", "b200q_program_add_argmax", "b200q_program_add_embed",
     "b200q_program_finalize", "b200q_program_launch", "b200q_program_free", "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free",
     "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
 ]
@@ -417,6 +417,24 @@ class Program:
 
     def swigluq(self, gate_up, F_: int, M: int, xq_out):
         _check(lib().b200q_program_add_swigluq(self._h, C.c_void_p(gate_up.data_ptr()), C.c_int64(F_), C.c_int64(M), C.c_void_p(xq_out.data_ptr())))
+        self.n_ops += 1
+
+    def attn(self, qkv, pos, ck, cv, rope, nh: int, nkv: int, hd: int, max_ctx: int, M: int, xq_out):
+        _check(lib().b200q_program_add_attn(self._h, C.c_void_p(qkv.data_ptr()), C.c_void_p(pos.data_ptr()), C.c_void_p(ck.data_ptr()),
+                                            C.c_void_p(cv.data_ptr()), C.c_void_p(rope.data_ptr()), C.c_int32(nh), C.c_int32(nkv), C.c_int32(hd),
+                                            C.c_int32(max_ctx), C.c_int64(M), C.c_void_p(xq_out.data_ptr())))
+        self.n_ops += 1
+
+    def argmax(self, logits, ids, pos):
+        M, V = logits.shape
+        _check(lib().b200q_program_add_argmax(self._h, C.c_void_p(logits.data_ptr()), C.c_int64(V), C.c_int64(M), C.c_void_p(ids.data_ptr()),
+                                              C.c_void_p(pos.data_ptr())))
+        self.n_ops += 2
+
+    def embed(self, table, ids, h):
+        M, H = h.shape
+        _check(lib().b200q_program_add_embed(self._h, C.c_void_p(table.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_int64(H), C.c_int64(M),
+                                             C.c_void_p(h.data_ptr())))
         self.n_ops += 1
 
     def finalize(self):

@@ -151,6 +151,10 @@ int32_t b200q_program_add_normq(b200q_program* p, const float* h_in, const float
 int32_t b200q_program_add_matvec(b200q_program* p, const b200q_weight* w, const void* xq, int64_t M, void* y, int32_t y_dtype, int64_t ldy,
                                  void* workspace, size_t workspace_bytes);
 int32_t b200q_program_add_swigluq(b200q_program* p, const float* gate_up, int64_t F, int64_t M, void* xq_out);
+int32_t b200q_program_add_attn(b200q_program* p, const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table,
+                               int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq_out);
+int32_t b200q_program_add_argmax(b200q_program* p, const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc);
+int32_t b200q_program_add_embed(b200q_program* p, const void* table_f16, const int64_t* ids, int64_t H, int64_t M, float* h);
 int32_t b200q_program_finalize(b200q_program* p);
 int32_t b200q_program_launch(const b200q_program* p, void* stream);
 int32_t b200q_program_free(b200q_program* p);

@@ -54,19 +54,21 @@ def test_gemm_vs_oracle(client, fmt, NKM):
 # A persistent kernel with grid barriers can hang if it is wrong, and a hung kernel cannot be interrupted by pytest: the test
 # only runs when asked for (B200Q_TEST_EXPERIMENTAL=1, under `timeout`), never in the default -m gpu suite.
 @pytest.mark.skipif(__import__("os").environ.get("B200Q_TEST_EXPERIMENTAL", "0") == "0", reason="experimental persistent kernel: opt-in (B200Q_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("mode", ["1", "2"])
 @pytest.mark.parametrize("scheme", ["Q6_K", "Q4_K_M", "Q8_0", "AWQ"])
-def test_dstep_programs_reproduce_the_launch_per_op_step(client, scheme, monkeypatch):
-    """B200Q_DSTEP=1: 3 launches per layer (program, attention, program) must give the same logits, bit for bit, as the
-    8 separate launches (identical arithmetic), over several dependent steps; then under CUDA-graph replay"""
+def test_dstep_programs_reproduce_the_launch_per_op_step(client, scheme, mode, monkeypatch):
+    """B200Q_DSTEP=1: 3 launches per layer (program, attention, program); B200Q_DSTEP=2: the whole step in ONE launch.
+    Both must give the same logits, bit for bit, as the 8 separate launches per layer (identical arithmetic), over several
+    dependent steps; then under CUDA-graph replay"""
     import numpy as np
     import torch
     from blazr_b200 import decode
     cfg = decode.PRESETS["tiny"]
     hm = decode.build_host_model(cfg, scheme, seed=31)
     ref = decode.Decoder(client, cfg, scheme, batch=1, max_ctx=64, host=hm)
-    monkeypatch.setenv("B200Q_DSTEP", "1")
+    monkeypatch.setenv("B200Q_DSTEP", mode)
     exp = decode.Decoder(client, cfg, scheme, batch=1, max_ctx=64, host=hm)
-    assert exp.programs is not None
+    assert (exp.programs is not None) if mode == "1" else (exp.step_program is not None)
     for d in (ref, exp):
         d.reset([3])
     for _ in range(6):
