@@ -49,6 +49,8 @@ static bool ggml_family(int ggml_type, FamilyInfo* fi) {
         case 10: *fi = {B200Q_FAM_Q2_K, 256, 84, 16, 128 * 84}; return true;
         case 11: *fi = {B200Q_FAM_Q3_K, 256, 110, 16, 128 * 110}; return true;
         case 23: *fi = {B200Q_FAM_IQ4_XS, 256, 136, 32, 128 * 136}; return true;
+        case 35: *fi = {B200Q_FAM_TQ2_0, 256, 66, 32, 128 * 66}; return true;
+        case 34: *fi = {B200Q_FAM_TQ2_0, 256, 54, 32, 128 * 66}; return true;              // TQ1_0 -> TQ2_0 layout (source adaptor)
         // source adaptors (formats.cuh): exact re-encodings into an existing family at upload
         case 2: *fi = {B200Q_FAM_G4, 32, 18, 32, 128 * 128 + 128 * 8 * 3}; return true;   // Q4_0  -> G4, 32-wide groups
         case 6: *fi = {B200Q_FAM_Q8_0, 32, 22, 32, 128 * 272}; return true;               // Q5_0  -> Q8_0 family

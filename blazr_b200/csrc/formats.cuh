@@ -637,6 +637,74 @@ struct FmtIQ4XS {
     }
 };
 
+// TQ2_0 : ternary, canonical [u8 qs[64]][f16 d]  (66 B / 256),  w = d (q - 1),  q = 2-bit code (same element order as Q2_K)
+// chunk: Q2 128x64 B (unit = 2 words) | D 128x2 B
+struct FmtTQ2_0 {
+    static constexpr int FAMILY = 14, SUB = 32;
+    static constexpr bool NIB = false;
+    static constexpr bool SIGNED = false;
+    static constexpr bool HAS_MIN = false;
+    static constexpr int Q2 = 0, D = 128 * 64;
+    __host__ __device__ static constexpr int chunk_bytes(int) { return 128 * 66; }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 66; }
+
+    // codes[256] (0..3) of one row-chunk + f16 bits of d -> planes
+    __device__ static void store_row(const uint8_t* codes, uint16_t dbits, uint8_t* chunk, int r) {
+        uint8_t* q2 = chunk + Q2 + r * 64;
+        for (int i = 0; i < 8; i++) store_2bit_unit(q2 + 8 * swzd(r, i), codes + 32 * i);
+        chunk[D + r * 2] = (uint8_t)(dbits & 0xFF);
+        chunk[D + r * 2 + 1] = (uint8_t)(dbits >> 8);
+    }
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t codes[256];
+        if (nvalid <= 0) {
+            for (int e = 0; e < 256; e++) codes[e] = 1;   // code 1 = value 0 (and d = 0)
+            store_row(codes, 0, chunk, r);
+            return;
+        }
+        for (int e = 0; e < 256; e++) {
+            const int n = e >> 7, l = (e & 127) >> 5, m = e & 31;
+            codes[e] = (src[32 * n + m] >> (2 * l)) & 3;
+        }
+        store_row(codes, (uint16_t)(src[64] | (src[65] << 8)), chunk, r);
+    }
+    template <bool SMEM, bool RAWHI = false>
+    __device__ __forceinline__ static void load_unit(const uint8_t* chunk, int r, int i, Unit& u, FmtMeta) {
+        const uint2 q = ld8<SMEM>(chunk + Q2 + r * 64 + 8 * swzd(r, i));
+        const uint32_t M2 = 0x03030303u;
+        u.v[0] = q.x & M2; u.v[1] = (q.x >> 2) & M2; u.v[2] = (q.x >> 4) & M2; u.v[3] = (q.x >> 6) & M2;
+        u.v[4] = q.y & M2; u.v[5] = (q.y >> 2) & M2; u.v[6] = (q.y >> 4) & M2; u.v[7] = (q.y >> 6) & M2;
+        u.a[0] = u.a[1] = half_bits_to_float(ld2(chunk + D + r * 2));
+        u.b[0] = u.b[1] = 0.0f;
+        u.off[0] = u.off[1] = 1;
+    }
+};
+
+// TQ1_0 : ternary, base-3 packed, canonical [u8 qs[48]][u8 qh[4]][f16 d]  (54 B / 256): re-encoded at upload into the
+// TQ2_0 layout (2-bit codes, 66 B / 256 on the device); trit n of byte x = ((uint8)(x * 3^n) * 3) >> 8
+struct SrcTQ1_0 {
+    __host__ __device__ static constexpr int chunk_bytes(int gpc) { return FmtTQ2_0::chunk_bytes(gpc); }
+    __host__ __device__ static constexpr int src_block_elems() { return 256; }
+    __host__ __device__ static constexpr int src_block_bytes() { return 54; }
+    __device__ static void repack_row(const uint8_t* src, int nvalid, uint8_t* chunk, int r, FmtMeta) {
+        uint8_t codes[256];
+        if (nvalid <= 0) {
+            for (int e = 0; e < 256; e++) codes[e] = 1;
+            FmtTQ2_0::store_row(codes, 0, chunk, r);
+            return;
+        }
+        const uint8_t pow3[5] = {1, 3, 9, 27, 81};
+        for (int n = 0; n < 5; n++)
+            for (int m = 0; m < 32; m++) codes[32 * n + m] = (uint8_t)(((uint32_t)(uint8_t)(src[m] * pow3[n]) * 3u) >> 8);
+        for (int n = 0; n < 5; n++)
+            for (int m = 0; m < 16; m++) codes[160 + 16 * n + m] = (uint8_t)(((uint32_t)(uint8_t)(src[32 + m] * pow3[n]) * 3u) >> 8);
+        for (int n = 0; n < 4; n++)
+            for (int m = 0; m < 4; m++) codes[240 + 4 * n + m] = (uint8_t)(((uint32_t)(uint8_t)(src[48 + m] * pow3[n]) * 3u) >> 8);
+        FmtTQ2_0::store_row(codes, (uint16_t)(src[52] | (src[53] << 8)), chunk, r);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Source adaptors: 32-element ggml block formats whose arithmetic is exactly expressible in an existing family are
 // re-encoded at upload and then run that family's kernels (no new compute code, dequantized weights and integer

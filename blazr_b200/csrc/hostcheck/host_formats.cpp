@@ -65,6 +65,7 @@ extern "C" int hostfmt_decompose(int ggml_type, const uint8_t* blocks, int64_t N
         case 10: return dump<FmtQ2K>(blocks, N, K, 1, q, a, b);
         case 11: return dump<FmtQ3K>(blocks, N, K, 1, q, a, b);
         case 23: return dump<FmtIQ4XS>(blocks, N, K, 1, q, a, b);
+        case 35: return dump<FmtTQ2_0>(blocks, N, K, 1, q, a, b);
         default: return -1;
     }
 }
@@ -84,6 +85,7 @@ extern "C" int hostfmt_decompose_adapted(int ggml_type, const uint8_t* blocks, i
         case 2: return dump_adapt<SrcQ4_0, FmtG4>(blocks, N, K, 8, q, a, b);
         case 6: return dump_adapt<SrcQ5_0, FmtQ8_0>(blocks, N, K, 1, q, a, b);
         case 20: return dump_adapt<SrcIQ4NL, FmtQ8_0>(blocks, N, K, 1, q, a, b);
+        case 34: return dump_adapt<SrcTQ1_0, FmtTQ2_0>(blocks, N, K, 1, q, a, b);
         default: return -1;
     }
 }

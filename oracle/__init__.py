@@ -23,10 +23,11 @@ _LIB_PATH = os.path.join(_HERE, "libquant_oracle.so")
 Q4_0, Q4_1, Q5_0, Q5_1, Q8_0 = 2, 3, 6, 7, 8
 Q2_K, Q3_K, Q4_K, Q5_K, Q6_K = 10, 11, 12, 13, 14
 IQ4_NL, IQ4_XS = 20, 23
+TQ1_0, TQ2_0 = 34, 35
 GGML_TYPES = {
     "Q4_0": Q4_0, "Q4_1": Q4_1, "Q5_0": Q5_0, "Q5_1": Q5_1, "Q8_0": Q8_0,
     "Q2_K": Q2_K, "Q3_K": Q3_K, "Q4_K": Q4_K, "Q5_K": Q5_K, "Q6_K": Q6_K,
-    "IQ4_NL": IQ4_NL, "IQ4_XS": IQ4_XS,
+    "IQ4_NL": IQ4_NL, "IQ4_XS": IQ4_XS, "TQ1_0": TQ1_0, "TQ2_0": TQ2_0,
 }
 
 

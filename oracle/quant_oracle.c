@@ -36,7 +36,7 @@
 enum {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ4_NL = 20, T_IQ4_XS = 23
+    T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
 };
 
 static const int8_t kvalues_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
@@ -71,7 +71,7 @@ static uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 int64_t orc_type_block_elems(int t) {
     switch (t) {
         case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: case T_IQ4_NL: return 32;
-        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: return QK_K;
+        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: return QK_K;
         default: return 0;
     }
 }
@@ -80,6 +80,7 @@ int64_t orc_type_block_bytes(int t) {
         case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24;
         case T_Q8_0: return 34; case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144;
         case T_Q5_K: return 176; case T_Q6_K: return 210; case T_IQ4_NL: return 18; case T_IQ4_XS: return 136;
+        case T_TQ1_0: return 54; case T_TQ2_0: return 66;
         default: return 0;
     }
 }
@@ -226,6 +227,26 @@ static void decompose_block(int t, const uint8_t* p, int8_t* qi, float* a, float
                     qi[32 * ib + 16 + j] = kvalues_iq4nl[qs[16 * ib + j] >> 4];
                 }
             }
+        } break;
+        case T_TQ2_0: { /* ternary, 2 bits: [u8 qs[64]][f16 d]; element 128 n + 32 l + m = ((qs[32 n + m] >> 2 l) & 3) - 1 */
+            float d = h2f(rd16(p + 64));
+            for (int sb = 0; sb < 8; sb++) { a[sb] = d; b[sb] = 0.0f; }
+            for (int e = 0; e < 256; e++) {
+                int n = e / 128, l = (e % 128) / 32, m = e % 32;
+                qi[e] = (int8_t)(((p[32 * n + m] >> (2 * l)) & 3) - 1);
+            }
+        } break;
+        case T_TQ1_0: { /* ternary, base 3: [u8 qs[48]][u8 qh[4]][f16 d]; 5 trits per qs byte, 4 per qh byte:
+                           trit n of byte x = ((uint8)(x * 3^n) * 3) >> 8 */
+            static const uint8_t pow3[5] = {1, 3, 9, 27, 81};
+            float d = h2f(rd16(p + 52));
+            for (int sb = 0; sb < 8; sb++) { a[sb] = d; b[sb] = 0.0f; }
+            for (int n = 0; n < 5; n++)
+                for (int m = 0; m < 32; m++) qi[32 * n + m] = (int8_t)((((uint16_t)(uint8_t)(p[m] * pow3[n])) * 3 >> 8) - 1);
+            for (int n = 0; n < 5; n++)
+                for (int m = 0; m < 16; m++) qi[160 + 16 * n + m] = (int8_t)((((uint16_t)(uint8_t)(p[32 + m] * pow3[n])) * 3 >> 8) - 1);
+            for (int n = 0; n < 4; n++)
+                for (int m = 0; m < 4; m++) qi[240 + 4 * n + m] = (int8_t)((((uint16_t)(uint8_t)(p[48 + m] * pow3[n])) * 3 >> 8) - 1);
         } break;
         default: break;
     }
