@@ -94,6 +94,7 @@ static cudaError_t gemm_launch_family(int family, const GemmParams& p, int grid,
         case B200Q_FAM_Q3_K: return gemm_launch<B200Q_FAM_Q3_K>(p, grid, smem, st);
         case B200Q_FAM_IQ4_XS: return gemm_launch<B200Q_FAM_IQ4_XS>(p, grid, smem, st);
         case B200Q_FAM_TQ2_0: return gemm_launch<B200Q_FAM_TQ2_0>(p, grid, smem, st);
+        case B200Q_FAM_I8S: return gemm_launch<B200Q_FAM_I8S>(p, grid, smem, st);
         case B200Q_FAM_G4: return gemm_launch<B200Q_FAM_G4>(p, grid, smem, st);
         default: return cudaErrorNotSupported;
     }

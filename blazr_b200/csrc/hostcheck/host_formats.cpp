@@ -86,6 +86,9 @@ extern "C" int hostfmt_decompose_adapted(int ggml_type, const uint8_t* blocks, i
         case 6: return dump_adapt<SrcQ5_0, FmtQ8_0>(blocks, N, K, 1, q, a, b);
         case 20: return dump_adapt<SrcIQ4NL, FmtQ8_0>(blocks, N, K, 1, q, a, b);
         case 34: return dump_adapt<SrcTQ1_0, FmtTQ2_0>(blocks, N, K, 1, q, a, b);
+        case 16: return dump_adapt<SrcIQ2XXS, FmtI8S>(blocks, N, K, 3, q, a, b);
+        case 17: return dump_adapt<SrcIQ2XS, FmtI8S>(blocks, N, K, 3, q, a, b);
+        case 18: return dump_adapt<SrcIQ3XXS, FmtI8S>(blocks, N, K, 2, q, a, b);
         default: return -1;
     }
 }

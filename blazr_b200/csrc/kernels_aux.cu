@@ -8,11 +8,14 @@ cudaError_t launch_repack_ggml(int family, const uint8_t* src, int64_t src_row_b
                                cudaStream_t st) {
     (void)family;
     // source adaptors (formats.cuh): ggml types re-encoded into an existing family
-    if (w->ggml_type == 2 || w->ggml_type == 6 || w->ggml_type == 20 || w->ggml_type == 34) {
+    if (w->ggml_type == 2 || w->ggml_type == 6 || w->ggml_type == 20 || w->ggml_type == 34 || (w->ggml_type >= 16 && w->ggml_type <= 18)) {
         dim3 grid((unsigned)w->KC, (unsigned)w->T);
         const FmtMeta meta{w->gpc};
         if (w->ggml_type == 2) repack_ggml_kernel<SrcQ4_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else if (w->ggml_type == 6) repack_ggml_kernel<SrcQ5_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else if (w->ggml_type == 16) repack_ggml_kernel<SrcIQ2XXS><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else if (w->ggml_type == 17) repack_ggml_kernel<SrcIQ2XS><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else if (w->ggml_type == 18) repack_ggml_kernel<SrcIQ3XXS><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else if (w->ggml_type == 34) repack_ggml_kernel<SrcTQ1_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else repack_ggml_kernel<SrcIQ4NL><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         count_launch();
@@ -152,6 +155,7 @@ cudaError_t launch_dequantize(const b200q_weight* w, void* out, int dtype, cudaS
         case B200Q_FAM_Q3_K: return dequant_launch<B200Q_FAM_Q3_K>(w, out, dtype, st);
         case B200Q_FAM_IQ4_XS: return dequant_launch<B200Q_FAM_IQ4_XS>(w, out, dtype, st);
         case B200Q_FAM_TQ2_0: return dequant_launch<B200Q_FAM_TQ2_0>(w, out, dtype, st);
+        case B200Q_FAM_I8S: return dequant_launch<B200Q_FAM_I8S>(w, out, dtype, st);
         case B200Q_FAM_G4: return dequant_launch<B200Q_FAM_G4>(w, out, dtype, st);
         default: return cudaErrorInvalidValue;
     }
@@ -237,6 +241,7 @@ cudaError_t launch_int_partials(const b200q_weight* w, const uint8_t* xq, int64_
         case B200Q_FAM_Q3_K: return partials_launch<B200Q_FAM_Q3_K>(w, xq, M, out, st);
         case B200Q_FAM_IQ4_XS: return partials_launch<B200Q_FAM_IQ4_XS>(w, xq, M, out, st);
         case B200Q_FAM_TQ2_0: return partials_launch<B200Q_FAM_TQ2_0>(w, xq, M, out, st);
+        case B200Q_FAM_I8S: return partials_launch<B200Q_FAM_I8S>(w, xq, M, out, st);
         case B200Q_FAM_G4: return partials_launch<B200Q_FAM_G4>(w, xq, M, out, st);
         default: return cudaErrorInvalidValue;
     }

@@ -42,6 +42,7 @@ static cudaError_t launch_family(int family, const MatvecParams& p, int mb, int 
         case B200Q_FAM_Q3_K: return mv_launch<B200Q_FAM_Q3_K>(p, mb, grid, smem, st);
         case B200Q_FAM_IQ4_XS: return mv_launch<B200Q_FAM_IQ4_XS>(p, mb, grid, smem, st);
         case B200Q_FAM_TQ2_0: return mv_launch<B200Q_FAM_TQ2_0>(p, mb, grid, smem, st);
+        case B200Q_FAM_I8S: return mv_launch<B200Q_FAM_I8S>(p, mb, grid, smem, st);
         case B200Q_FAM_G4: return mv_launch<B200Q_FAM_G4>(p, mb, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }

@@ -63,7 +63,7 @@ typedef enum b200q_dtype { B200Q_F32 = 0, B200Q_F16 = 1, B200Q_BF16 = 2, B200Q_F
 typedef enum b200q_family {
     B200Q_FAM_Q4_K = 1, B200Q_FAM_Q6_K = 2, B200Q_FAM_Q8_0 = 3, B200Q_FAM_G4 = 4 /* AWQ/GPTQ */,
     B200Q_FAM_Q5_K = 5, B200Q_FAM_Q4_0 = 6, B200Q_FAM_Q4_1 = 7, B200Q_FAM_Q5_0 = 8, B200Q_FAM_Q5_1 = 9,
-    B200Q_FAM_Q2_K = 10, B200Q_FAM_Q3_K = 11, B200Q_FAM_IQ4_NL = 12, B200Q_FAM_IQ4_XS = 13, B200Q_FAM_TQ2_0 = 14
+    B200Q_FAM_Q2_K = 10, B200Q_FAM_Q3_K = 11, B200Q_FAM_IQ4_NL = 12, B200Q_FAM_IQ4_XS = 13, B200Q_FAM_TQ2_0 = 14, B200Q_FAM_I8S = 15 /* decoded family of the grid-coded IQ formats */
 } b200q_family;
 
 /* source kinds */

@@ -29,6 +29,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include "iq_grids.h"  /* generated: public ggml IQ codebooks (tools/gen_iq_grids.py) */
 
 #define QK_K 256
 
@@ -36,7 +37,7 @@
 enum {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
 };
 
 static const int8_t kvalues_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
@@ -71,7 +72,7 @@ static uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 int64_t orc_type_block_elems(int t) {
     switch (t) {
         case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: case T_IQ4_NL: return 32;
-        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: return QK_K;
+        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: return QK_K;
         default: return 0;
     }
 }
@@ -80,7 +81,7 @@ int64_t orc_type_block_bytes(int t) {
         case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24;
         case T_Q8_0: return 34; case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144;
         case T_Q5_K: return 176; case T_Q6_K: return 210; case T_IQ4_NL: return 18; case T_IQ4_XS: return 136;
-        case T_TQ1_0: return 54; case T_TQ2_0: return 66;
+        case T_TQ1_0: return 54; case T_TQ2_0: return 66; case T_IQ2_XXS: return 66; case T_IQ2_XS: return 74; case T_IQ3_XXS: return 98;
         default: return 0;
     }
 }
@@ -88,6 +89,7 @@ int64_t orc_type_block_bytes(int t) {
 int orc_type_sub(int t) {
     switch (t) {
         case T_Q2_K: case T_Q3_K: case T_Q6_K: return 16;
+        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: return 16;  /* reported at 16 (IQ2_XS's native granularity) for all grid formats */
         default: return 32;
     }
 }
@@ -225,6 +227,49 @@ static void decompose_block(int t, const uint8_t* p, int8_t* qi, float* a, float
                 for (int j = 0; j < 16; j++) {
                     qi[32 * ib + j] = kvalues_iq4nl[qs[16 * ib + j] & 0xF];
                     qi[32 * ib + 16 + j] = kvalues_iq4nl[qs[16 * ib + j] >> 4];
+                }
+            }
+        } break;
+        case T_IQ2_XXS: { /* [f16 d][8 x (u32 grid indices, u32 4 x 7-bit sign index | 4-bit scale << 28)]; gguf.quants.IQ2_XXS */
+            float d = h2f(rd16(p));
+            for (int ib = 0; ib < 8; ib++) {
+                uint32_t q0 = rd32(p + 2 + 8 * ib), q1 = rd32(p + 2 + 8 * ib + 4);
+                float db = (d * (0.5f + (float)(q1 >> 28))) * 0.25f;
+                a[2 * ib] = a[2 * ib + 1] = db; b[2 * ib] = b[2 * ib + 1] = 0.0f;
+                for (int l = 0; l < 4; l++) {
+                    const uint8_t* g = iq2xxs_grid[(q0 >> (8 * l)) & 0xFF];
+                    uint8_t sg = iq_ksigns[(q1 >> (7 * l)) & 127];
+                    for (int j = 0; j < 8; j++) qi[32 * ib + 8 * l + j] = (int8_t)(((sg >> j) & 1) ? -(int)g[j] : (int)g[j]);
+                }
+            }
+        } break;
+        case T_IQ2_XS: { /* [f16 d][u16 qs[32]: 9-bit grid index | 7-bit sign index << 9][u8 scales[8]: two 4-bit scales, one per 16] */
+            float d = h2f(rd16(p));
+            const uint8_t* sc = p + 2 + 64;
+            for (int sb = 0; sb < 16; sb++) {
+                int s4 = (sc[sb / 2] >> (4 * (sb % 2))) & 0xF;
+                a[sb] = (d * (0.5f + (float)s4)) * 0.25f; b[sb] = 0.0f;
+            }
+            for (int i = 0; i < 32; i++) {
+                uint16_t q = rd16(p + 2 + 2 * i);
+                const uint8_t* g = iq2xs_grid[q & 511];
+                uint8_t sg = iq_ksigns[q >> 9];
+                for (int j = 0; j < 8; j++) qi[8 * i + j] = (int8_t)(((sg >> j) & 1) ? -(int)g[j] : (int)g[j]);
+            }
+        } break;
+        case T_IQ3_XXS: { /* [f16 d][u8 qs[64] grid indices (4 values each)][8 x u32: 4 x 7-bit sign index | 4-bit scale << 28] */
+            float d = h2f(rd16(p));
+            const uint8_t* qs = p + 2;
+            for (int ib = 0; ib < 8; ib++) {
+                uint32_t q1 = rd32(p + 2 + 64 + 4 * ib);
+                float db = (d * (0.5f + (float)(q1 >> 28))) * 0.5f;
+                a[2 * ib] = a[2 * ib + 1] = db; b[2 * ib] = b[2 * ib + 1] = 0.0f;
+                for (int l = 0; l < 4; l++) {
+                    uint8_t sg = iq_ksigns[(q1 >> (7 * l)) & 127];
+                    for (int j = 0; j < 8; j++) {
+                        int v = iq3xxs_grid[qs[8 * ib + 2 * l + (j >> 2)]][j & 3];
+                        qi[32 * ib + 8 * l + j] = (int8_t)(((sg >> j) & 1) ? -v : v);
+                    }
                 }
             }
         } break;
