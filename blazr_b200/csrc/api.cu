@@ -54,6 +54,8 @@ static bool ggml_family(int ggml_type, FamilyInfo* fi) {
         case 16: *fi = {B200Q_FAM_I8S, 256, 66, 16, 128 * 274}; return true;   // IQ2_XXS
         case 17: *fi = {B200Q_FAM_I8S, 256, 74, 16, 128 * 274}; return true;   // IQ2_XS
         case 18: *fi = {B200Q_FAM_I8S, 256, 98, 16, 128 * 274}; return true;   // IQ3_XXS
+        case 22: *fi = {B200Q_FAM_I8S, 256, 82, 16, 128 * 274}; return true;   // IQ2_S
+        case 21: *fi = {B200Q_FAM_I8S, 256, 110, 16, 128 * 274}; return true;  // IQ3_S
         case 34: *fi = {B200Q_FAM_TQ2_0, 256, 54, 32, 128 * 66}; return true;              // TQ1_0 -> TQ2_0 layout (source adaptor)
         // source adaptors (formats.cuh): exact re-encodings into an existing family at upload
         case 2: *fi = {B200Q_FAM_G4, 32, 18, 32, 128 * 128 + 128 * 8 * 3}; return true;   // Q4_0  -> G4, 32-wide groups
@@ -177,6 +179,8 @@ int32_t b200q_weight_from_ggml_shard(int32_t ggml_type, const void* blocks, int3
     w->gpc = ggml_type == 2 ? 8 : 1;
     if (ggml_type == 16 || ggml_type == 17) w->gpc = 3;  // I8S: scale exponent (w = d * m * 2^-gpc * v)
     if (ggml_type == 18) w->gpc = 2;
+    if (ggml_type == 22) w->gpc = 3;
+    if (ggml_type == 21) w->gpc = 0;
     w->group_size = ggml_type == 2 ? 32 : 0;
     w->chunk_bytes = fi.chunk_bytes;
     w->canonical_bytes = w->N * (w->K / fi.block_elems) * fi.block_bytes;

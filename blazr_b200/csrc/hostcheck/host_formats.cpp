@@ -89,6 +89,8 @@ extern "C" int hostfmt_decompose_adapted(int ggml_type, const uint8_t* blocks, i
         case 16: return dump_adapt<SrcIQ2XXS, FmtI8S>(blocks, N, K, 3, q, a, b);
         case 17: return dump_adapt<SrcIQ2XS, FmtI8S>(blocks, N, K, 3, q, a, b);
         case 18: return dump_adapt<SrcIQ3XXS, FmtI8S>(blocks, N, K, 2, q, a, b);
+        case 22: return dump_adapt<SrcIQ2S, FmtI8S>(blocks, N, K, 3, q, a, b);
+        case 21: return dump_adapt<SrcIQ3S, FmtI8S>(blocks, N, K, 0, q, a, b);
         default: return -1;
     }
 }

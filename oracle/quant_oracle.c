@@ -37,7 +37,7 @@
 enum {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
 };
 
 static const int8_t kvalues_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
@@ -72,7 +72,7 @@ static uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 int64_t orc_type_block_elems(int t) {
     switch (t) {
         case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: case T_IQ4_NL: return 32;
-        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: return QK_K;
+        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: case T_IQ2_S: case T_IQ3_S: return QK_K;
         default: return 0;
     }
 }
@@ -82,6 +82,7 @@ int64_t orc_type_block_bytes(int t) {
         case T_Q8_0: return 34; case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144;
         case T_Q5_K: return 176; case T_Q6_K: return 210; case T_IQ4_NL: return 18; case T_IQ4_XS: return 136;
         case T_TQ1_0: return 54; case T_TQ2_0: return 66; case T_IQ2_XXS: return 66; case T_IQ2_XS: return 74; case T_IQ3_XXS: return 98;
+        case T_IQ2_S: return 82; case T_IQ3_S: return 110;
         default: return 0;
     }
 }
@@ -89,7 +90,7 @@ int64_t orc_type_block_bytes(int t) {
 int orc_type_sub(int t) {
     switch (t) {
         case T_Q2_K: case T_Q3_K: case T_Q6_K: return 16;
-        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: return 16;  /* reported at 16 (IQ2_XS's native granularity) for all grid formats */
+        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: case T_IQ2_S: case T_IQ3_S: return 16;  /* reported at 16 (IQ2_XS's native granularity) for all grid formats */
         default: return 32;
     }
 }
@@ -270,6 +271,35 @@ static void decompose_block(int t, const uint8_t* p, int8_t* qi, float* a, float
                         int v = iq3xxs_grid[qs[8 * ib + 2 * l + (j >> 2)]][j & 3];
                         qi[32 * ib + 8 * l + j] = (int8_t)(((sg >> j) & 1) ? -v : v);
                     }
+                }
+            }
+        } break;
+        case T_IQ2_S: { /* [f16 d][u8 qs[32]][u8 signs[32]][u8 qh[8]][u8 scales[8]]: 10-bit grid index = qs | 2 bits of qh << 8 */
+            float d = h2f(rd16(p));
+            const uint8_t* qs = p + 2; const uint8_t* sg = p + 34; const uint8_t* qh = p + 66; const uint8_t* sc = p + 74;
+            for (int sb = 0; sb < 16; sb++) {
+                int s4 = (sc[sb / 2] >> (4 * (sb % 2))) & 0xF;
+                a[sb] = (d * (0.5f + (float)s4)) * 0.25f; b[sb] = 0.0f;
+            }
+            for (int i = 0; i < 32; i++) {
+                int idx = qs[i] | (((qh[i / 4] >> (2 * (i % 4))) & 3) << 8);
+                const uint8_t* g = iq2s_grid[idx];
+                for (int j = 0; j < 8; j++) qi[8 * i + j] = (int8_t)(((sg[i] >> j) & 1) ? -(int)g[j] : (int)g[j]);
+            }
+        } break;
+        case T_IQ3_S: { /* [f16 d][u8 qs[64]][u8 qh[8]][u8 signs[32]][u8 scales[4]]: 9-bit grid index = qs | 1 bit of qh << 8 */
+            float d = h2f(rd16(p));
+            const uint8_t* qs = p + 2; const uint8_t* qh = p + 66; const uint8_t* sg = p + 74; const uint8_t* sc = p + 106;
+            for (int ib = 0; ib < 8; ib++) {
+                int s4 = (sc[ib / 2] >> (4 * (ib % 2))) & 0xF;
+                a[2 * ib] = a[2 * ib + 1] = d * (float)(1 + 2 * s4); b[2 * ib] = b[2 * ib + 1] = 0.0f;
+            }
+            for (int i = 0; i < 64; i++) {
+                int idx = qs[i] | (((qh[i / 8] >> (i % 8)) & 1) << 8);
+                const uint8_t* g = iq3s_grid[idx];
+                for (int j = 0; j < 4; j++) {
+                    int e = 4 * i + j;
+                    qi[e] = (int8_t)(((sg[e / 8] >> (e % 8)) & 1) ? -(int)g[j] : (int)g[j]);
                 }
             }
         } break;
