@@ -56,6 +56,8 @@ static bool ggml_family(int ggml_type, FamilyInfo* fi) {
         case 18: *fi = {B200Q_FAM_I8S, 256, 98, 16, 128 * 274}; return true;   // IQ3_XXS
         case 22: *fi = {B200Q_FAM_I8S, 256, 82, 16, 128 * 274}; return true;   // IQ2_S
         case 21: *fi = {B200Q_FAM_I8S, 256, 110, 16, 128 * 274}; return true;  // IQ3_S
+        case 19: *fi = {B200Q_FAM_I8S, 256, 50, 16, 128 * 274}; return true;   // IQ1_S
+        case 29: *fi = {B200Q_FAM_I8S, 256, 56, 16, 128 * 274}; return true;   // IQ1_M
         case 34: *fi = {B200Q_FAM_TQ2_0, 256, 54, 32, 128 * 66}; return true;              // TQ1_0 -> TQ2_0 layout (source adaptor)
         // source adaptors (formats.cuh): exact re-encodings into an existing family at upload
         case 2: *fi = {B200Q_FAM_G4, 32, 18, 32, 128 * 128 + 128 * 8 * 3}; return true;   // Q4_0  -> G4, 32-wide groups
@@ -181,6 +183,7 @@ int32_t b200q_weight_from_ggml_shard(int32_t ggml_type, const void* blocks, int3
     if (ggml_type == 18) w->gpc = 2;
     if (ggml_type == 22) w->gpc = 3;
     if (ggml_type == 21) w->gpc = 0;
+    if (ggml_type == 19 || ggml_type == 29) w->gpc = 3;
     w->group_size = ggml_type == 2 ? 32 : 0;
     w->chunk_bytes = fi.chunk_bytes;
     w->canonical_bytes = w->N * (w->K / fi.block_elems) * fi.block_bytes;

@@ -91,6 +91,8 @@ extern "C" int hostfmt_decompose_adapted(int ggml_type, const uint8_t* blocks, i
         case 18: return dump_adapt<SrcIQ3XXS, FmtI8S>(blocks, N, K, 2, q, a, b);
         case 22: return dump_adapt<SrcIQ2S, FmtI8S>(blocks, N, K, 3, q, a, b);
         case 21: return dump_adapt<SrcIQ3S, FmtI8S>(blocks, N, K, 0, q, a, b);
+        case 19: return dump_adapt<SrcIQ1S, FmtI8S>(blocks, N, K, 3, q, a, b);
+        case 29: return dump_adapt<SrcIQ1M, FmtI8S>(blocks, N, K, 3, q, a, b);
         default: return -1;
     }
 }

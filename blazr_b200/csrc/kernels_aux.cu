@@ -8,7 +8,7 @@ cudaError_t launch_repack_ggml(int family, const uint8_t* src, int64_t src_row_b
                                cudaStream_t st) {
     (void)family;
     // source adaptors (formats.cuh): ggml types re-encoded into an existing family
-    if (w->ggml_type == 2 || w->ggml_type == 6 || w->ggml_type == 20 || w->ggml_type == 34 || (w->ggml_type >= 16 && w->ggml_type <= 18) || w->ggml_type == 21 || w->ggml_type == 22) {
+    if (w->ggml_type == 2 || w->ggml_type == 6 || w->ggml_type == 20 || w->ggml_type == 34 || (w->ggml_type >= 16 && w->ggml_type <= 18) || w->ggml_type == 21 || w->ggml_type == 22 || w->ggml_type == 19 || w->ggml_type == 29) {
         dim3 grid((unsigned)w->KC, (unsigned)w->T);
         const FmtMeta meta{w->gpc};
         if (w->ggml_type == 2) repack_ggml_kernel<SrcQ4_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
@@ -18,6 +18,8 @@ cudaError_t launch_repack_ggml(int family, const uint8_t* src, int64_t src_row_b
         else if (w->ggml_type == 18) repack_ggml_kernel<SrcIQ3XXS><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else if (w->ggml_type == 22) repack_ggml_kernel<SrcIQ2S><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else if (w->ggml_type == 21) repack_ggml_kernel<SrcIQ3S><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else if (w->ggml_type == 19) repack_ggml_kernel<SrcIQ1S><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
+        else if (w->ggml_type == 29) repack_ggml_kernel<SrcIQ1M><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else if (w->ggml_type == 34) repack_ggml_kernel<SrcTQ1_0><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         else repack_ggml_kernel<SrcIQ4NL><<<grid, 128, 0, st>>>(src, src_row_bytes, n0, k0, w->N, w->K, w->KC, w->data, meta);
         count_launch();

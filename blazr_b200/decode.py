@@ -142,6 +142,8 @@ def random_ggml_device(fmt: str, N: int, K: int, seed: int, device) -> torch.Ten
     d_off, m_off, ratio, std1 = synth._FIELDS[t]
     sigma = 1.0 / (std1 * float(np.sqrt(K)))
     d = ((torch.rand(nb, device=device, generator=g) + 0.5) * sigma).to(torch.float16)
+    if t == 29:
+        raise NotImplementedError("IQ1_M keeps d in scattered nibbles: use synth.random_ggml (host) for it")
     for o in d_off:
         blk[:, o:o + 2] = d.view(torch.uint8).reshape(nb, 2)
     if m_off:

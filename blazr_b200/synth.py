@@ -14,7 +14,7 @@ GGML = {
     "Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8,
     "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14,
     "IQ4_NL": 20, "IQ4_XS": 23, "TQ1_0": 34, "TQ2_0": 35,
-    "IQ2_XXS": 16, "IQ2_XS": 17, "IQ3_XXS": 18, "IQ3_S": 21, "IQ2_S": 22,
+    "IQ2_XXS": 16, "IQ2_XS": 17, "IQ3_XXS": 18, "IQ3_S": 21, "IQ2_S": 22, "IQ1_S": 19, "IQ1_M": 29,
 }
 GGML_NAME = {v: k for k, v in GGML.items()}
 # (block elems, block bytes)
@@ -22,7 +22,7 @@ GGML_SIZES = {
     2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34),
     10: (256, 84), 11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210),
     20: (32, 18), 23: (256, 136), 34: (256, 54), 35: (256, 66),
-    16: (256, 66), 17: (256, 74), 18: (256, 98), 21: (256, 110), 22: (256, 82),
+    16: (256, 66), 17: (256, 74), 18: (256, 98), 21: (256, 110), 22: (256, 82), 19: (256, 50), 29: (256, 56),
 }
 # per type: (byte offsets of f16 d fields, byte offsets of f16 min fields, min/d ratio that zeroes the
 # mean of W, std of W at d = 1 with that ratio) -- measured once with uniform payload bytes.
@@ -32,7 +32,8 @@ _FIELDS = {
     12: ([0], [2], 7.5, 259.2), 13: ([0], [2], 15.55, 527.5), 14: ([208], [], 0.0, 1363.9),
     20: ([0], [], 0.0, 67.3), 23: ([0], [], 0.0, 1249.0), 34: ([52], [], 0.0, 0.82), 35: ([64], [], 0.0, 1.22),
     16: ([0], [], 0.0, 53.1), 17: ([0], [], 0.0, 55.8), 18: ([0], [], 0.0, 142.7),
-    21: ([0], [], 0.0, 140.3), 22: ([0], [], 0.0, 56.5),
+    21: ([0], [], 0.0, 140.3), 22: ([0], [], 0.0, 56.5), 19: ([0], [], 0.0, 7.21),
+    29: ([], [], 0.0, 7.21),  # IQ1_M: the f16 d is scattered over the top nibbles of its four u16 scale words (set_iq1m_d)
 }
 
 
@@ -47,6 +48,16 @@ def ggml_bytes_per_weight(t: int) -> float:
     return bb / be
 
 
+def set_iq1m_d(blk: np.ndarray, d: np.ndarray) -> None:
+    """IQ1_M keeps its f16 super-block scale in the top nibbles of the four u16 scale words (bytes 48..55):
+    d = s0 >> 12 | (s1 >> 8) & 0xF0 | (s2 >> 4) & 0xF00 | s3 & 0xF000.  blk: uint8 [nb, 56] (modified in place)."""
+    bits = np.ascontiguousarray(d, dtype=np.float16).view(np.uint16).astype(np.uint16)
+    sc = blk[:, 48:56].copy().view(np.uint16)
+    for i, sh in enumerate((0, 4, 8, 12)):
+        sc[:, i] = (sc[:, i] & np.uint16(0x0FFF)) | (((bits >> np.uint16(sh)) & np.uint16(0xF)) << np.uint16(12))
+    blk[:, 48:56] = sc.view(np.uint8)
+
+
 def random_ggml(t: int, N: int, K: int, seed: int = 0, gain: float = 1.0) -> np.ndarray:
     """Random raw ggml blocks for a logical [N, K] weight (row-major rows of K/block blocks)."""
     be, bb = GGML_SIZES[t]
@@ -58,6 +69,8 @@ def random_ggml(t: int, N: int, K: int, seed: int = 0, gain: float = 1.0) -> np.
     d = (rng.uniform(0.5, 1.5, size=nb) * sigma).astype(np.float16)
     for o in d_off:
         blk[:, o:o + 2] = d.view(np.uint8).reshape(nb, 2)
+    if t == 29:
+        set_iq1m_d(blk, d)
     if m_off:
         m = (d.astype(np.float32) * ratio).astype(np.float16)
         for o in m_off:

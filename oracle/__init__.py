@@ -26,11 +26,12 @@ IQ4_NL, IQ4_XS = 20, 23
 TQ1_0, TQ2_0 = 34, 35
 IQ2_XXS, IQ2_XS, IQ3_XXS = 16, 17, 18
 IQ3_S, IQ2_S = 21, 22
+IQ1_S, IQ1_M = 19, 29
 GGML_TYPES = {
     "Q4_0": Q4_0, "Q4_1": Q4_1, "Q5_0": Q5_0, "Q5_1": Q5_1, "Q8_0": Q8_0,
     "Q2_K": Q2_K, "Q3_K": Q3_K, "Q4_K": Q4_K, "Q5_K": Q5_K, "Q6_K": Q6_K,
     "IQ4_NL": IQ4_NL, "IQ4_XS": IQ4_XS, "TQ1_0": TQ1_0, "TQ2_0": TQ2_0,
-    "IQ2_XXS": IQ2_XXS, "IQ2_XS": IQ2_XS, "IQ3_XXS": IQ3_XXS, "IQ2_S": IQ2_S, "IQ3_S": IQ3_S,
+    "IQ2_XXS": IQ2_XXS, "IQ2_XS": IQ2_XS, "IQ3_XXS": IQ3_XXS, "IQ2_S": IQ2_S, "IQ3_S": IQ3_S, "IQ1_S": IQ1_S, "IQ1_M": IQ1_M,
 }
 
 

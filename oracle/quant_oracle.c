@@ -37,7 +37,7 @@
 enum {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ1_S = 19, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ1_M = 29, T_IQ4_NL = 20, T_IQ4_XS = 23, T_TQ1_0 = 34, T_TQ2_0 = 35
 };
 
 static const int8_t kvalues_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
@@ -72,7 +72,7 @@ static uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 int64_t orc_type_block_elems(int t) {
     switch (t) {
         case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: case T_IQ4_NL: return 32;
-        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: case T_IQ2_S: case T_IQ3_S: return QK_K;
+        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: case T_IQ4_XS: case T_TQ1_0: case T_TQ2_0: case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: case T_IQ2_S: case T_IQ3_S: case T_IQ1_S: case T_IQ1_M: return QK_K;
         default: return 0;
     }
 }
@@ -82,7 +82,7 @@ int64_t orc_type_block_bytes(int t) {
         case T_Q8_0: return 34; case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144;
         case T_Q5_K: return 176; case T_Q6_K: return 210; case T_IQ4_NL: return 18; case T_IQ4_XS: return 136;
         case T_TQ1_0: return 54; case T_TQ2_0: return 66; case T_IQ2_XXS: return 66; case T_IQ2_XS: return 74; case T_IQ3_XXS: return 98;
-        case T_IQ2_S: return 82; case T_IQ3_S: return 110;
+        case T_IQ2_S: return 82; case T_IQ3_S: return 110; case T_IQ1_S: return 50; case T_IQ1_M: return 56;
         default: return 0;
     }
 }
@@ -90,7 +90,7 @@ int64_t orc_type_block_bytes(int t) {
 int orc_type_sub(int t) {
     switch (t) {
         case T_Q2_K: case T_Q3_K: case T_Q6_K: return 16;
-        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: case T_IQ2_S: case T_IQ3_S: return 16;  /* reported at 16 (IQ2_XS's native granularity) for all grid formats */
+        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ3_XXS: case T_IQ2_S: case T_IQ3_S: case T_IQ1_S: case T_IQ1_M: return 16;  /* reported at 16 (IQ2_XS's native granularity) for all grid formats */
         default: return 32;
     }
 }
@@ -301,6 +301,39 @@ static void decompose_block(int t, const uint8_t* p, int8_t* qi, float* a, float
                     int e = 4 * i + j;
                     qi[e] = (int8_t)(((sg[e / 8] >> (e % 8)) & 1) ? -(int)g[j] : (int)g[j]);
                 }
+            }
+        } break;
+        case T_IQ1_S: { /* [f16 d][u8 qs[32]][u16 qh[8]]: per 32: 3-bit scale (bits 12-14), delta sign (bit 15), 4 x 11-bit grid index;
+                           w = d (2 s + 1) (g + delta), delta = +-1/8  ==>  integer form: v = 8 g +- 1, a = d (2 s + 1) / 8 (all exact) */
+            float d = h2f(rd16(p));
+            const uint8_t* qs = p + 2;
+            for (int ib = 0; ib < 8; ib++) {
+                uint16_t qh = rd16(p + 34 + 2 * ib);
+                float dl = d * (float)(2 * ((qh >> 12) & 7) + 1);
+                a[2 * ib] = a[2 * ib + 1] = dl * 0.125f; b[2 * ib] = b[2 * ib + 1] = 0.0f;
+                int dsign = (qh & 0x8000) ? -1 : 1;
+                for (int l = 0; l < 4; l++) {
+                    const int8_t* g = iq1s_grid[qs[4 * ib + l] | (((qh >> (3 * l)) & 7) << 8)];
+                    for (int j = 0; j < 8; j++) qi[32 * ib + 8 * l + j] = (int8_t)(8 * g[j] + dsign);
+                }
+            }
+        } break;
+        case T_IQ1_M: { /* [u8 qs[32]][u8 qh[16]][u16 scales[4]]: f16 d scattered over the top nibbles of the scale words, a 3-bit scale
+                           per 16, per 8 elements an 11-bit grid index (qs | 3 bits of a qh nibble << 8) and a delta sign (bit 3 of the nibble) */
+            const uint8_t* qs = p; const uint8_t* qh = p + 32;
+            uint16_t sc[4];
+            for (int i = 0; i < 4; i++) sc[i] = rd16(p + 48 + 2 * i);
+            uint16_t dbits = (uint16_t)((sc[0] >> 12) | ((sc[1] >> 8) & 0x00F0) | ((sc[2] >> 4) & 0x0F00) | (sc[3] & 0xF000));
+            float d = h2f(dbits);
+            for (int sb = 0; sb < 16; sb++) {
+                int s3 = (sc[sb / 4] >> (3 * (sb % 4))) & 7;
+                a[sb] = (d * (float)(2 * s3 + 1)) * 0.125f; b[sb] = 0.0f;
+            }
+            for (int i = 0; i < 32; i++) {
+                int nib = (qh[i / 2] >> (4 * (i % 2))) & 0xF;
+                const int8_t* g = iq1s_grid[qs[i] | ((nib & 7) << 8)];
+                int dsign = (nib & 8) ? -1 : 1;
+                for (int j = 0; j < 8; j++) qi[8 * i + j] = (int8_t)(8 * g[j] + dsign);
             }
         } break;
         case T_TQ2_0: { /* ternary, 2 bits: [u8 qs[64]][f16 d]; element 128 n + 32 l + m = ((qs[32 n + m] >> 2 l) & 3) - 1 */

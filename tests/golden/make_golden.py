@@ -40,6 +40,9 @@ def main():
             for j in range(bb):
                 if j not in keep:
                     flat[blk_i, j] = fill
+        if t == 29:  # IQ1_M: restore the scattered f16 scale of the two extreme-payload blocks
+            keep_d = np.array([0.02, 0.03], dtype=np.float16)
+            synth.set_iq1m_d(flat[:2], keep_d)
         qt = gguf.GGMLQuantizationType(t)
         deq = quants.dequantize(flat.reshape(N, -1), qt).astype(np.float32)
         assert deq.shape == (N, K)

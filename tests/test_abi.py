@@ -57,7 +57,7 @@ def test_invalid_arguments_return_codes_not_crashes():
     h = C.c_void_p()
     blocks = np.zeros(144, dtype=np.uint8)
     # unsupported ggml type -> UNSUPPORTED (no CPU fallback), message mentions it
-    rc = L.b200q_weight_from_ggml(C.c_int32(19), C.c_void_p(blocks.ctypes.data), C.c_int32(0), C.c_int64(1), C.c_int64(256),
+    rc = L.b200q_weight_from_ggml(C.c_int32(9), C.c_void_p(blocks.ctypes.data), C.c_int32(0), C.c_int64(1), C.c_int64(256),
                                   C.c_int32(0), None, C.byref(h))
     assert rc == -2 and b"no CPU fallback" in L.b200q_last_error()
     # K not a multiple of the block

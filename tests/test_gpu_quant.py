@@ -258,7 +258,7 @@ def test_errors_are_codes(client):
         client.quant_matmul(x, c.w, workspace=torch.zeros(256, dtype=torch.uint8, device="cuda"))
     assert e.value.code == -4
     with pytest.raises(ops.B200QError) as e:
-        client.weight_from_ggml(19, np.zeros(50, dtype=np.uint8), 1, 256)  # IQ1_S: no kernel, no fallback
+        client.weight_from_ggml(9, np.zeros(288, dtype=np.uint8), 1, 256)  # Q8_1 (activation-side format): no kernel, no fallback
     assert e.value.code == -2
     qw, sc, zr = synth.random_awq(128, 256)
     sc = sc * np.float32(1.0001)  # no longer f16-representable

@@ -28,7 +28,7 @@ def hostlib():
 
 
 NATIVE = ["Q4_K", "Q6_K", "Q8_0", "Q5_K", "Q4_1", "Q5_1", "Q2_K", "Q3_K", "IQ4_XS", "TQ2_0"]
-ADAPTED = ["Q4_0", "Q5_0", "IQ4_NL", "TQ1_0", "IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S"]
+ADAPTED = ["Q4_0", "Q5_0", "IQ4_NL", "TQ1_0", "IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ1_S", "IQ1_M"]
 
 
 def _device_decompose(lib, name, blocks, N, K):

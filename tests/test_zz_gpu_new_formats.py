@@ -1,4 +1,4 @@
-"""GPU parity of the formats added after the GPU budget of round 1 was spent: Q5_K, Q4_1, Q5_1, Q2_K, Q3_K, IQ4_XS, TQ2_0, TQ1_0, IQ2_XXS, IQ2_XS, IQ3_XXS, IQ2_S, IQ3_S.
+"""GPU parity of the formats added after the GPU budget of round 1 was spent: Q5_K, Q4_1, Q5_1, Q2_K, Q3_K, IQ4_XS, TQ2_0, TQ1_0, IQ2_XXS, IQ2_XS, IQ3_XXS, IQ2_S, IQ3_S, IQ1_S, IQ1_M.
 
 Their format-specific code (repack_row / load_unit in formats.cuh) is verified bit for bit on the CPU
 (tests/test_host_formats.py); every kernel they run through is format-generic and green on hardware for the other nine
@@ -13,7 +13,7 @@ import test_gpu_quant as tq
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: CPU-verified layouts, not yet run on hardware")]
 
-NEW = ["Q5_K", "Q4_1", "Q5_1", "Q2_K", "Q3_K", "IQ4_XS", "TQ2_0", "TQ1_0", "IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S"]
+NEW = ["Q5_K", "Q4_1", "Q5_1", "Q2_K", "Q3_K", "IQ4_XS", "TQ2_0", "TQ1_0", "IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ1_S", "IQ1_M"]
 
 
 @pytest.mark.parametrize("name", NEW)
