@@ -339,3 +339,47 @@ def load_gguf(client, path: str, batch: int = 1, max_ctx: int = 512, tp_rank: in
     hm = host_model_from_gguf(g, client)
     dec = Decoder(client, hm.cfg, hm.scheme, batch=batch, max_ctx=max_ctx, host=hm, tp_rank=tp_rank, tp_world=tp_world, group=group)
     return dec, hm.cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# MoE expert tensors (reference executor_cache.rs:218-228: experts are stored STACKED [num_experts, ...] and sliced per
+# expert).  GGUF stores them as 3-D tensors blk.N.ffn_{gate,up,down}_exps.weight with ne = (K, N, E): E consecutive
+# [N, K] matrices of packed blocks.
+# ------------------------------------------------------------------------------------------------
+def expert_rows(g: Gguf, name: str) -> List[np.ndarray]:
+    """per-expert [N, row_bytes] uint8 views of a stacked expert tensor (zero-copy)"""
+    ti = g.tensor_info(name)
+    if len(ti.shape) != 3:
+        raise GgufError(f"{name}: expected a 3-D stacked expert tensor, got shape {ti.shape}")
+    K, N, E = ti.shape
+    rows = g.tensor_rows(name)            # [E * N, row_bytes]
+    if rows.shape[0] != E * N:
+        raise GgufError(f"{name}: {rows.shape[0]} rows for {E} experts of {N} rows")
+    return [rows[e * N:(e + 1) * N] for e in range(E)]
+
+
+def host_experts_from_gguf(g: Gguf, layer: int):
+    """[(gate_up_blocks [2 ffn, row_bytes], gate_up_type, down_blocks [hidden, row_bytes], down_type)] per expert: gate and up are
+    fused row-wise (gate rows first), which is what the decode path launches once (ops.ExpertWeights.gate_up)"""
+    p = f"blk.{layer}."
+    tg, tu, td = (g.tensor_info(p + n + ".weight") for n in ("ffn_gate_exps", "ffn_up_exps", "ffn_down_exps"))
+    if tg.ggml_type != tu.ggml_type or tg.shape != tu.shape:
+        raise GgufError(f"layer {layer}: gate and up expert tensors differ in type or shape (cannot fuse)")
+    gate, up, down = (expert_rows(g, p + n + ".weight") for n in ("ffn_gate_exps", "ffn_up_exps", "ffn_down_exps"))
+    if not (len(gate) == len(up) == len(down)):
+        raise GgufError(f"layer {layer}: expert counts differ")
+    return [(np.concatenate([gate[e], up[e]], axis=0), tg.ggml_type, down[e], td.ggml_type) for e in range(len(gate))]
+
+
+def moe_mlp_from_gguf(client, g: Gguf, layer: int):
+    """ops.MoeMlp for one MoE layer of a GGUF file (hidden = K of gate, ffn = N of gate)"""
+    from . import ops
+
+    p = f"blk.{layer}."
+    hidden, ffn, _ = g.tensor_info(p + "ffn_gate_exps.weight").shape
+    experts = []
+    for gu_blocks, gt, dn_blocks, dt in host_experts_from_gguf(g, layer):
+        gu = client.weight_from_ggml(gt, np.ascontiguousarray(gu_blocks), 2 * ffn, hidden)
+        dn = client.weight_from_ggml(dt, np.ascontiguousarray(dn_blocks), hidden, ffn)
+        experts.append(ops.ExpertWeights(gu, dn))
+    return ops.MoeMlp(client, experts, ffn, hidden)

@@ -85,3 +85,32 @@ def test_malformed_files_raise(tmp_path, tiny_file):
     g = gguf_loader.Gguf.open(path)
     with pytest.raises(gguf_loader.GgufError):
         g.tensor_info("no.such.tensor")
+
+
+def test_stacked_expert_tensors(tmp_path):
+    """3-D ffn_*_exps tensors (ne = K, N, E) -> per-expert row views; gate and up fused row-wise per expert"""
+    from blazr_b200 import synth
+    E, hidden, ffn = 4, 256, 128
+    tq4, tq8 = synth.GGML["Q4_K"], synth.GGML["Q8_0"]
+    gate = [synth.random_ggml(tq4, ffn, hidden, seed=10 + e) for e in range(E)]
+    up = [synth.random_ggml(tq4, ffn, hidden, seed=20 + e) for e in range(E)]
+    down = [synth.random_ggml(tq8, hidden, ffn, seed=30 + e) for e in range(E)]
+    path = str(tmp_path / "moe.gguf")
+    w = gguf.GGUFWriter(path, "llama")
+    w.add_block_count(1)
+    w.add_expert_count(E)
+    QT = gguf.GGMLQuantizationType
+    for name, mats, qt in (("ffn_gate_exps", gate, QT.Q4_K), ("ffn_up_exps", up, QT.Q4_K), ("ffn_down_exps", down, QT.Q8_0)):
+        stacked = np.ascontiguousarray(np.stack(mats, axis=0))          # [E, N, row_bytes]
+        w.add_tensor(f"blk.0.{name}.weight", stacked, raw_shape=stacked.shape, raw_dtype=qt)
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    g = gguf_loader.Gguf.open(path)
+    assert g.tensor_info("blk.0.ffn_gate_exps.weight").shape == (hidden, ffn, E)
+    assert g.tensor_info("blk.0.ffn_down_exps.weight").shape == (ffn, hidden, E)
+    ex = gguf_loader.host_experts_from_gguf(g, 0)
+    assert len(ex) == E
+    for e, (gu_b, gt, dn_b, dt) in enumerate(ex):
+        assert (gt, dt) == (tq4, tq8)
+        assert np.array_equal(gu_b[:ffn], gate[e]) and np.array_equal(gu_b[ffn:], up[e]) and np.array_equal(dn_b, down[e])
+    assert gguf_loader.get_gguf_info(path).is_moe
+    assert gguf_loader.hf_name("blk.0.ffn_gate_exps.weight") == "model.layers.0.mlp.experts.gate_proj.weight"
