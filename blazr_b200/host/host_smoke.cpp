@@ -72,10 +72,17 @@ int main() {
         }
         if (maxerr / maxref > 1e-2) { printf("matmul rel err %g\n", maxerr / maxref); return 1; }
         // errors are codes, not crashes
-        try { client.weight_from_ggml(16, blocks.data(), false, 1, 256); return 1; } catch (const BackendError& e) { if (e.code != B200Q_ERR_UNSUPPORTED) return 1; }
+        // (ggml type 9 = Q8_1 is an activation-side format: it has no weight kernel and never will)
+        try {
+            client.weight_from_ggml(9, blocks.data(), false, 1, 256);
+            printf("weight_from_ggml(type 9 / Q8_1) succeeded, expected B200Q_ERR_UNSUPPORTED\n");
+            return 1;
+        } catch (const BackendError& e) {
+            if (e.code != B200Q_ERR_UNSUPPORTED) { printf("weight_from_ggml(type 9): error code %d, expected B200Q_ERR_UNSUPPORTED (%d)\n", (int)e.code, (int)B200Q_ERR_UNSUPPORTED); return 1; }
+        }
         TensorParallelState tp{2, 3};
         auto r = tp.shard_range(10);
-        if (r.first != 7 || r.second != 10) return 1;  // reference tensor_parallel.rs:186
+        if (r.first != 7 || r.second != 10) { printf("shard_range(10) at rank 2 of 3 = [%lld, %lld), expected [7, 10)\n", (long long)r.first, (long long)r.second); return 1; }  // reference tensor_parallel.rs:186
         printf("host_smoke ok: dequant bit-exact, matmul rel err %.2e\n", maxerr / maxref);
         return 0;
     } catch (const std::exception& e) {
