@@ -206,10 +206,10 @@ def run_b200(args):
     prompt = rng.integers(0, cfg.vocab, size=(M, args.prompt))
     dec.reset(prompt[:, 0])
     for s in range(args.prompt - 1):  # feed the prompt through decode steps (keeps the KV cache realistic)
-        g.replay()
+        dec.replay()
         dec.ids.copy_(torch.from_numpy(prompt[:, s + 1]).to(dev))
     for _ in range(max(3, args.warmup)):
-        g.replay()
+        dec.replay()
 
     # ---- device-resident throughput: K graph replays between events ----
     sampler = ClockSampler(local)
@@ -220,7 +220,7 @@ def run_b200(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        g.replay()
+        dec.replay()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -235,7 +235,7 @@ def run_b200(args):
     e2.record()
     for _ in range(args.steps):
         dec.ids.copy_(pin_in, non_blocking=True)   # H2D: this step's input token ids
-        g.replay()
+        dec.replay()
         pin_out.copy_(dec.ids, non_blocking=True)  # D2H: the sampled token ids
         torch.cuda.current_stream().synchronize()  # the host needs the token before it can issue the next step
         pin_in.copy_(pin_out)

@@ -7,6 +7,7 @@
 #include <new>
 #include <vector>
 
+#include "comm_dev.cuh"
 #include "common.cuh"
 #include "internal.h"
 
@@ -26,6 +27,16 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+namespace b200q {
+// the same thread-local message for the other translation units (comm.cu, decode_ops.cu)
+int32_t set_error(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace b200q
 static int32_t cuda_fail(cudaError_t e, const char* what) {
     return fail(B200Q_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
@@ -347,6 +358,13 @@ int32_t b200q_weight_set_bias(b200q_weight* w, const float* bias, int32_t src_on
     return B200Q_OK;
 }
 
+int32_t b200q_weight_set_next(b200q_weight* w, const b200q_weight* next) {
+    if (!w) return fail(B200Q_ERR_INVALID_ARG, "null weight");
+    if (next && next->device != w->device) return fail(B200Q_ERR_INVALID_ARG, "successor lives on device %d, weight on device %d", next->device, w->device);
+    w->next = next;
+    return B200Q_OK;
+}
+
 // ---- compute ----
 size_t b200q_act_bytes(int64_t K, int64_t M) {
     int64_t kc = (K + CHUNK_K - 1) / CHUNK_K;
@@ -377,6 +395,31 @@ int32_t b200q_matmul_q8(const b200q_weight* w, const void* xq, int64_t M, void* 
     if (workspace_bytes < align256(matvec_ws_bytes(w, M))) return fail(B200Q_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, align256(matvec_ws_bytes(w, M)));
     CUDA_TRY(launch_matvec(w, (const uint8_t*)xq, M, y, y_dtype, ldy, (uint8_t*)workspace, (cudaStream_t)stream));
     return B200Q_OK;
+}
+
+// ---- fused tensor-parallel exchange, producer side (comm_dev.cuh): the matvec stores its finished row sums into every rank's buffer ----
+static int32_t matmul_q8_remote(const b200q_weight* w, const void* xq, int64_t M, b200q_comm* c, int mode, int64_t ld, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (!w || !xq || !c || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+    if (M < 1 || M > 4) return fail(B200Q_ERR_UNSUPPORTED, "fused-exchange matvec handles M in [1,4] (got %lld)", (long long)M);
+    if (ld < w->N) return fail(B200Q_ERR_INVALID_ARG, "row stride %lld < N = %lld", (long long)ld, (long long)w->N);
+    const int64_t cap = mode == RP_ALLREDUCE ? comm_slot_elems(c) : comm_gather_elems(c);
+    if (M * ld > cap) return fail(B200Q_ERR_INVALID_ARG, "M * ld = %lld exceeds the communicator's %s capacity %lld", (long long)(M * ld), mode == RP_ALLREDUCE ? "slot" : "gather", (long long)cap);
+    if (comm_device(c) != w->device) return fail(B200Q_ERR_INVALID_ARG, "communicator on device %d, weight on device %d", comm_device(c), w->device);
+    if (workspace_bytes < align256(matvec_ws_bytes(w, M))) return fail(B200Q_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, align256(matvec_ws_bytes(w, M)));
+    RemoteOut ro;
+    ro.mode = mode;
+    if (!comm_dev(c, &ro.comm)) return fail(B200Q_ERR_INVALID_ARG, "communicator not connected");
+    CUDA_TRY(launch_matvec(w, (const uint8_t*)xq, M, nullptr, B200Q_F64, ld, (uint8_t*)workspace, (cudaStream_t)stream, nullptr, &ro));
+    return B200Q_OK;
+}
+
+int32_t b200q_matmul_q8_rowpar(const b200q_weight* w, const void* xq, int64_t M, b200q_comm* c, int64_t ld, void* workspace, size_t workspace_bytes, void* stream) {
+    return matmul_q8_remote(w, xq, M, c, RP_ALLREDUCE, ld, workspace, workspace_bytes, stream);
+}
+
+int32_t b200q_matmul_q8_gather(const b200q_weight* w, const void* xq, int64_t M, b200q_comm* c, int64_t ld, void* workspace, size_t workspace_bytes, void* stream) {
+    return matmul_q8_remote(w, xq, M, c, RP_ALLGATHER, ld, workspace, workspace_bytes, stream);
 }
 
 // ---- expert banks (MoE) ----

@@ -5,10 +5,19 @@
 // next matvec consumes (so no separate quantise pass runs).  Every kernel is PDL-aware: it lets its
 // dependents launch immediately (the following matvec prefetches weights meanwhile) and waits for its own
 // producers before touching global memory.
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+#include "comm_dev.cuh"
 #include "common.cuh"
 #include "internal.h"
 
 namespace b200q {
+
+// sticky per-device error word raised by kernels that detect an argument they cannot honour without corrupting
+// memory (they write nothing and return); read and cleared by b200q_decode_error()
+__device__ int g_decode_error = 0;
+constexpr int B200Q_DECODE_ERR_POSITION = 1;  // attention: pos[m] outside [0, max_ctx)
 
 // ---- shared: quantise 256 values held one per thread (thread t <-> k = kc*256 + t) into a record ----
 __device__ __forceinline__ void quant_store_record(float v, uint8_t* rec, int t) {
@@ -99,6 +108,72 @@ __global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cluster form of the same operator, and the CONSUMER of the fused tensor-parallel exchange (comm_dev.cuh):
+//     delta = f32( sum over ranks, in rank order, of the f64 partial row sums the row-parallel matvec pushed )   [TP]
+//     h_out = h_in (+ delta) ; xq = quant(rmsnorm(h_out) * w)
+// One thread-block CLUSTER per token row, one column per thread (1024 columns per CTA, up to 8 CTAs = H <= 8192): the row
+// is read once (instead of once per 256-column CTA), the sum of squares is combined through distributed shared memory
+// in CTA order (f64: order-independent up to 1e-16, same bits as the oracle), and each warp quantises its own 32-block.
+// TP: the kernel first polls the `world` epoch flags in its own memory; the reduced delta never exists in HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int NORMC_NT = 1024;
+__global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(const CommDev c, const float* __restrict__ h_in, const float* __restrict__ delta,
+                                                                             float* __restrict__ h_out, const float* __restrict__ w, float eps, int H, int M,
+                                                                             uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_launch_dependents();
+    const int cta = blockIdx.x, ncta = gridDim.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int k = cta * NORMC_NT + t;
+    const bool active = k < H;
+    __shared__ double red[NORMC_NT / 32];
+    __shared__ double cta_part;   // this CTA's share of the sum of squares (read by every CTA of the cluster)
+    __shared__ float s_inv;
+    const float wk = active ? w[k] : 0.0f;  // static weights: fetched before the dependency wait
+    pdl_wait();
+    float v = 0.0f;
+    if (c.world > 0) {
+        // the producing matvec of THIS rank completed before the wait returned: its epoch is published; peers may lag
+        const uint8_t* mine = c.peers[c.rank];
+        const unsigned int epoch = __ldcg(reinterpret_cast<const unsigned int*>(mine + COMM_OFF_AR_EPOCH));
+        const int par = (int)(epoch & 1u);
+        comm_wait_flags(c, COMM_OFF_AR_FLAGS, par, epoch, t);
+        __syncthreads();
+        if (active) {
+            double s = 0.0;
+            for (int r = 0; r < c.world; r++) s += __ldcg(reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + (size_t)m * H + k);
+            v = __fadd_rn(h_in[(size_t)m * H + k], (float)s);
+        }
+    } else if (active) {
+        v = h_in[(size_t)m * H + k];
+        if (delta) v = __fadd_rn(v, delta[(size_t)m * H + k]);
+    }
+    double ss = (double)v * (double)v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (warp == 0) {
+        double p = red[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) cta_part = p;
+    }
+    cluster.sync();
+    if (warp == 0) {
+        double tot = 0.0;
+        for (int r = 0; r < ncta; r++) tot += *cluster.map_shared_rank(&cta_part, r);  // CTA order: identical on every CTA
+        if (lane == 0) s_inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)H), eps)));
+    }
+    cluster.sync();  // (also keeps every CTA's shared memory alive until its peers have read it)
+    if (!active) return;
+    h_out[(size_t)m * H + k] = v;
+    const float x = __fmul_rn(__fmul_rn(v, s_inv), wk);
+    if (xnorm) xnorm[(size_t)m * H + k] = x;
+    if (xq) quant_store_record(x, xq + ((size_t)(k / CHUNK_K) * M + m) * ACT_REC_BYTES, k % CHUNK_K);
+}
+
+// ------------------------------------------------------------------------------------------------
 // act = silu(gate) * up ; xq = quant(act)       gate_up: [M, 2*F] (gate first), F % 32 == 0; the records are
 // zero-padded up to the next multiple of 256 (DeepSeek-V2-Lite experts: F = 1408 = 5.5 chunks)
 // ------------------------------------------------------------------------------------------------
@@ -132,7 +207,12 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
     extern __shared__ float s_sc[];  // scores, then probabilities, for positions 0..p
     const int head = blockIdx.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int kvh = head / (nh / nkv);
-    const int p = pos[m];
+    // a position outside the cache (host bookkeeping bug, or a graph replayed past max_ctx) must never index the
+    // RoPE table, the KV cache or the score buffer: loads ahead of the wait use a clamped position, and after the
+    // wait the CTA raises the sticky device error flag (b200q_decode_error) and writes nothing
+    const int p_raw = pos[m];
+    const bool bad_pos = p_raw < 0 || p_raw >= max_ctx;
+    const int p = bad_pos ? 0 : p_raw;
     const int row = (nh + 2 * nkv) * HD;
     const float* qsrc = qkv + (size_t)m * row + (size_t)head * HD;
     const float* ksrc = qkv + (size_t)m * row + (size_t)(nh + kvh) * HD;
@@ -147,8 +227,10 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
     __shared__ float s_redf[NW];
     __shared__ double s_redd[NW];
     // ---- before griddepcontrol.wait: everything that does not depend on the qkv matvec running just ahead of this
-    // kernel -- pos (advanced by the previous step's argmax), the RoPE row and the cached K / V rows j < p (written by
-    // earlier steps) -- is pulled into registers, so only the new q/k/v load remains on the critical path after it.
+    // kernel -- pos (advanced by the previous step's argmax; stable here because embed_kernel, the first kernel of
+    // every step, releases its dependents only after that argmax completed), the RoPE row and the cached K / V rows
+    // j < p (written by earlier steps) -- is pulled into registers, so only the new q/k/v load remains on the
+    // critical path after it.
     constexpr int QE = HD / 4;          // score pass: elements per thread (4 threads per position)
     constexpr int EG = HD / 4;          // output pass: element groups of 4
     constexpr int JG = ATT_NT / EG;     // output pass: position groups (16 for hd 128, 32 for hd 64)
@@ -171,6 +253,10 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
         if (t < HD / 2) { rc = rt[2 * t]; rs = rt[2 * t + 1]; }
     }
     pdl_wait();
+    if (bad_pos) {
+        if (t == 0) atomicOr(&g_decode_error, B200Q_DECODE_ERR_POSITION);
+        return;
+    }
     if (t < HD / 2) {
         const float c = rc, sn = rs;
         const float q0 = qsrc[2 * t], q1 = qsrc[2 * t + 1];
@@ -326,10 +412,58 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
     }
 }
 
-// embedding gather: h[m, :] = table[ids[m], :] (f16 table -> f32)
-__global__ void embed_kernel(const __half* __restrict__ table, const int64_t* __restrict__ ids, int H, float* __restrict__ h) {
+// Consumer of the fused lm_head all-gather (comm_dev.cuh): rank r's logits for row m live at gather[r][m * vs + j] and are
+// vocabulary id r * vs + j (columns no rank wrote stay -inf).  Waits for every rank's flag, then the same arg-max.
+__global__ void __launch_bounds__(1024) argmax_gathered_kernel(const CommDev c, int vs, int M, int64_t* __restrict__ out, int* __restrict__ pos_inc) {
     pdl_launch_dependents();
     pdl_wait();
+    const int m = blockIdx.x, t = threadIdx.x;
+    const uint8_t* mine = c.peers[c.rank];
+    const unsigned int epoch = __ldcg(reinterpret_cast<const unsigned int*>(mine + COMM_OFF_AG_EPOCH));
+    comm_wait_flags(c, COMM_OFF_AG_FLAGS, 0, epoch, t);
+    __syncthreads();
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int r = 0; r < c.world; r++) {
+        const float* row = reinterpret_cast<const float*>(mine + comm_ag_off(c, r)) + (size_t)m * vs;
+        for (int j = t; j < vs; j += 1024) {
+            const float v = __ldcg(row + j);
+            const int i = r * vs + j;
+            if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+        }
+    }
+    __shared__ float sv[32];
+    __shared__ int si[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((t & 31) == 0) { sv[t >> 5] = best; si[t >> 5] = bi; }
+    __syncthreads();
+    if (t < 32) {
+        best = sv[t]; bi = si[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (t == 0) {
+            out[m] = bi;
+            if (pos_inc) pos_inc[m] += 1;
+        }
+    }
+}
+
+// embedding gather: h[m, :] = table[ids[m], :] (f16 table -> f32)
+// First kernel of a decode step: it releases its dependents only AFTER its own dependency wait, which breaks the
+// programmatic chain at the step boundary -- nothing of step s+1 (in particular the attention prologue, which reads
+// pos[] ahead of its wait) can start before step s's argmax has advanced pos[] and written the token ids.
+__global__ void embed_kernel(const __half* __restrict__ table, const int64_t* __restrict__ ids, int H, float* __restrict__ h) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int m = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < H) h[(size_t)m * H + k] = __half2float(table[(size_t)ids[m] * H + k]);
@@ -341,13 +475,61 @@ using namespace b200q;
 
 extern "C" {
 
+static cudaError_t launch_norm_cluster(const CommDev& c, const float* h_in, const float* delta, float* h_out, const float* w, float eps, int64_t H, int64_t M,
+                                       void* xq, float* xnorm, cudaStream_t st) {
+    const unsigned ncta = (unsigned)((H + NORMC_NT - 1) / NORMC_NT);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncta, (unsigned)M);
+    cfg.blockDim = dim3(NORMC_NT);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = ncta;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, add_rmsnorm_quant_cluster_kernel, (const CommDev)c, h_in, delta, h_out, w, eps, (int)H, (int)M, (uint8_t*)xq, xnorm);
+    count_launch();
+    return e;
+}
+
 int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_out, const float* w, float eps, int64_t H, int64_t M, void* xq,
                                 float* xnorm, void* stream) {
     if (!h_in || !h_out || !w || (!xq && !xnorm) || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
     if (delta && h_in == h_out) return B200Q_ERR_INVALID_ARG;  // CTAs re-read the whole input row: no in-place update
+    static const bool old_kernel = [] { const char* e_ = getenv("B200Q_NORM_OLD"); return e_ && atoi(e_) != 0; }();
+    if (H <= 8 * NORMC_NT && !old_kernel) {  // one cluster per row: the row is read once
+        cudaError_t e = launch_norm_cluster(CommDev{}, h_in, delta, h_out, w, eps, H, M, xq, xnorm, (cudaStream_t)stream);
+        return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+    }
     cudaError_t e = launch_pdl(add_rmsnorm_quant_kernel, dim3((unsigned)(H / CHUNK_K), (unsigned)M), dim3(NORM_NT), 0, (cudaStream_t)stream, h_in, delta,
                                h_out, w, eps, (int)H, (int)M, (uint8_t*)xq, xnorm);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+/* Consumer of b200q_matmul_q8_rowpar: h_out = h_in + allreduce(partials); xq = quant(rmsnorm(h_out) * w); the reduced
+ * delta is summed in rank order from the communicator's slots (identical bits on every rank, equal to the 1-GPU sum). */
+int32_t b200q_allreduce_add_rmsnorm_quant(b200q_comm* comm, const float* h_in, float* h_out, const float* w, float eps, int64_t H, int64_t M, void* xq,
+                                          float* xnorm, void* stream) {
+    if (!comm || !h_in || !h_out || !w || (!xq && !xnorm) || H <= 0 || H % CHUNK_K || M <= 0) return set_error(B200Q_ERR_INVALID_ARG, "allreduce_add_rmsnorm_quant: bad arguments");
+    if (H > 8 * NORMC_NT) return set_error(B200Q_ERR_UNSUPPORTED, "allreduce_add_rmsnorm_quant: H = %lld > %d", (long long)H, 8 * NORMC_NT);
+    if (M * H > comm_slot_elems(comm)) return set_error(B200Q_ERR_INVALID_ARG, "allreduce_add_rmsnorm_quant: M * H = %lld exceeds the communicator's slot capacity %lld", (long long)(M * H), (long long)comm_slot_elems(comm));
+    CommDev c;
+    if (!comm_dev(comm, &c)) return set_error(B200Q_ERR_INVALID_ARG, "allreduce_add_rmsnorm_quant: communicator not connected");
+    cudaError_t e = launch_norm_cluster(c, h_in, nullptr, h_out, w, eps, H, M, xq, xnorm, (cudaStream_t)stream);
+    return e == cudaSuccess ? B200Q_OK : set_error(B200Q_ERR_CUDA, "allreduce_add_rmsnorm_quant launch: %s", cudaGetErrorString(e));
+}
+
+/* Consumer of b200q_matmul_q8_gather: greedy token over the gathered [world][M][vs] logits */
+int32_t b200q_argmax_gathered(b200q_comm* comm, int64_t vs, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream) {
+    if (!comm || !out_ids || vs <= 0 || M <= 0 || M * vs > comm_gather_elems(comm)) return set_error(B200Q_ERR_INVALID_ARG, "argmax_gathered: bad arguments");
+    CommDev c;
+    if (!comm_dev(comm, &c)) return set_error(B200Q_ERR_INVALID_ARG, "argmax_gathered: communicator not connected");
+    cudaError_t e = launch_pdl(argmax_gathered_kernel, dim3((unsigned)M), dim3(1024), 0, (cudaStream_t)stream, (const CommDev)c, (int)vs, (int)M, out_ids, (int*)pos_inc);
+    return e == cudaSuccess ? B200Q_OK : set_error(B200Q_ERR_CUDA, "argmax_gathered launch: %s", cudaGetErrorString(e));
 }
 
 int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream) {
@@ -386,6 +568,20 @@ int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, 
         return B200Q_ERR_UNSUPPORTED;
     }
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+/* Reads and clears the sticky device error word of the CURRENT device (synchronises the device: call it outside
+ * graph capture, e.g. once per generate()).  0 = no error; bit 0 = a decode-attention position was outside [0, max_ctx). */
+int32_t b200q_decode_error(int32_t* out_flags) {
+    if (!out_flags) return B200Q_ERR_INVALID_ARG;
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_decode_error, sizeof(int)) != cudaSuccess) return B200Q_ERR_CUDA;
+    if (v != 0) {
+        const int zero = 0;
+        if (cudaMemcpyToSymbol(g_decode_error, &zero, sizeof(int)) != cudaSuccess) return B200Q_ERR_CUDA;
+    }
+    *out_flags = v;
+    return B200Q_OK;
 }
 
 int32_t b200q_argmax(const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream) {

@@ -16,6 +16,7 @@ struct b200q_weight {
     float* bias;    // device f32 [N] or null
     int32_t* perm;  // device i32 [K] (GPTQ act-order) or null
     int num_sms;
+    const b200q_weight* next;  // successor hint (b200q_weight_set_next), not owned; null = none
 };
 
 // Expert bank (boostr::ExpertWeights stacked [num_experts, ...]): E weights of one format and shape
@@ -63,11 +64,20 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int 
 size_t matvec_ws_bytes(const b200q_weight* w, int64_t M);  // counters + partials (excludes the activation buffer)
 void set_matvec_trace(long long* dev_buf);
 cudaError_t launch_l2_prefetch(const b200q_weight* w, int64_t M, int64_t max_bytes, cudaStream_t st);
+struct RemoteOut;  // fused TP exchange target (comm_dev.cuh: mode + CommDev)
 cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
-                          const FusedPrologue* fp = nullptr);
+                          const FusedPrologue* fp = nullptr, const RemoteOut* ro = nullptr);
 size_t matvec_grouped_ws_bytes(const b200q_bank* b, int64_t n_slots);
 cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const uint8_t* xq, int64_t x_rows, int64_t x_slot_div,
                                   void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st);
+
+// ---- comm.cu ----
+struct CommDev;
+bool comm_dev(const b200q_comm* c, CommDev* d);  // false when a peer is not connected yet
+int64_t comm_slot_elems(const b200q_comm* c);
+int64_t comm_gather_elems(const b200q_comm* c);
+int comm_device(const b200q_comm* c);
+int32_t set_error(int32_t code, const char* fmt, ...);  // api.cu: thread-local b200q_last_error message
 
 // ---- gemm_tc.cu ----
 size_t gemm_ws_bytes(const b200q_weight* w, int64_t M);

@@ -69,7 +69,7 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int 
     if (nst < 2) return cudaErrorInvalidValue;
     int64_t C = w->T * w->KC;
     int64_t G = (int64_t)w->num_sms;
-    if (const char* e = getenv("B200Q_MV_GRID")) { int v = atoi(e); if (v >= 1) G = v; }
+    if (const char* e = getenv("B200Q_MV_GRID")) { int v = atoi(e); if (v >= 1 && v <= w->num_sms) G = v; }  // ws_part holds num_sms slots
     if (G > C) G = C;
     plan->grid = (int)G;
     plan->nstages = nst;
@@ -89,7 +89,7 @@ size_t matvec_ws_bytes(const b200q_weight* w, int64_t M) {
 }
 
 cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
-                          const FusedPrologue* fp) {
+                          const FusedPrologue* fp, const RemoteOut* ro) {
     MatvecPlan plan;
     const int pro = fp ? fp->mode : 0;
     cudaError_t e = matvec_plan(w, M, &plan, pro);
@@ -128,6 +128,29 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.y_slot_stride = 0;
     p.trace = g_trace ? g_trace + (size_t)(g_trace_launch++) * 148 * 8 : nullptr;
     p.debug_flags = 0;
+    p.rp_mode = ro ? ro->mode : RP_NONE;
+    if (ro) p.comm = ro->comm;
+    else p.comm = CommDev{};
+    p.next_w = nullptr;
+    p.next_C = p.next_KC = 0;
+    p.next_chunk_bytes = p.next_G = p.next_pf = 0;
+    if (w->next && w->next->device == w->device && !pro) {
+        // successor prefetch budget: what HBM can deliver during this launch's tail + the boundary (~6 us ~ 40 MB), well
+        // inside the 126 MB L2.  B200Q_MV_NEXT_PF_MB overrides (0 disables).
+        static const double pf_mb = [] { const char* e = getenv("B200Q_MV_NEXT_PF_MB"); return e ? atof(e) : 32.0; }();
+        MatvecPlan np_;
+        if (pf_mb > 0 && matvec_plan(w->next, M, &np_, 0) == cudaSuccess) {
+            const int64_t per_cta = (int64_t)(pf_mb * 1048576.0) / ((int64_t)np_.grid * w->next->chunk_bytes);
+            if (per_cta >= 1) {
+                p.next_w = w->next->data;
+                p.next_C = w->next->T * w->next->KC;
+                p.next_KC = w->next->KC;
+                p.next_chunk_bytes = w->next->chunk_bytes;
+                p.next_G = np_.grid;
+                p.next_pf = per_cta > 4096 ? 4096 : (int)per_cta;
+            }
+        }
+    }
     {
         // L2 prefetch budget: at most ~64 MB per launch so a huge weight (lm_head) cannot thrash the 126 MB L2
         int64_t per_cta = (64ll << 20) / ((int64_t)plan.grid * p.chunk_bytes);
@@ -178,6 +201,8 @@ cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, i
     p.x_rows = (int)x_rows;
     p.x_slot_div = (int)x_slot_div;
     p.y_slot_stride = y_slot_stride;
+    p.next_w = nullptr;
+    p.next_pf = 0;
     return launch_family(v.family, p, 1, plan.grid, plan.smem_bytes, st);
 }
 

@@ -1,5 +1,6 @@
 // matvec_common.cuh -- parameters and stream-K helpers shared by the matvec kernel and its host dispatcher.
 #pragma once
+#include "comm_dev.cuh"
 #include "formats.cuh"
 #include "internal.h"
 #include "streamk_plan.cuh"
@@ -43,6 +44,17 @@ struct MatvecParams {
     // weight w_table[sel[s]], the activation record row s / x_slot_div of xq (x_rows rows per k-chunk) and writes
     // y[s * y_slot_stride + n].  Tiles are numbered slot-major (tile t -> slot t / tpw), so the stream-K split, the
     // partial slots and the fix-up work unchanged on the concatenated chunk range.
+    // successor hint (b200q_weight_set_next): once this CTA's own chunks are all requested, its producer asks the TMA
+    // engine to pull the first next_pf chunks of every successor CTA range (in that CTA's processing order) into L2, so
+    // HBM keeps streaming through this launch's tail, the kernel boundary and whatever glue operators run in between
+    const uint8_t* next_w;
+    int64_t next_C, next_KC;
+    int next_chunk_bytes, next_G, next_pf;
+    // fused tensor-parallel exchange (comm_dev.cuh): RP_ALLREDUCE = finished row sums (f64) go to slot (parity, rank) of every
+    // rank's buffer instead of y; RP_ALLGATHER = f32 outputs go to region `rank` of every rank's gather area.  Index inside
+    // the slot / region = m * ldy + n.  The last CTA of the launch raises this rank's epoch flag at every peer.
+    int rp_mode;
+    CommDev comm;
     const uint8_t* const* w_table;
     const int32_t* sel;
     int tpw;              // tiles per weight

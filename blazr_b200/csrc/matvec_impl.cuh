@@ -127,6 +127,36 @@ __device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* x
     named_bar_sync(4, NT);  // records visible to every consumer warp
 }
 
+// ---- output of one finished row sum: local y, or (fused TP exchange) the same element of every rank's slot ----
+struct RpState {
+    unsigned int epoch;  // epoch of this exchange (previous + 1)
+    size_t off;          // byte offset of this rank's slot / gather region inside every rank's buffer
+};
+__device__ __forceinline__ RpState rp_begin(const MatvecParams& p) {
+    RpState r{0u, 0};
+    if (p.rp_mode == RP_NONE) return r;
+    const uint8_t* mine = p.comm.peers[p.comm.rank];
+    const bool ar = p.rp_mode == RP_ALLREDUCE;
+    // written by the last CTA of the previous exchange of this kind; that launch completed before griddepcontrol.wait returned
+    r.epoch = __ldcg(reinterpret_cast<const unsigned int*>(mine + (ar ? COMM_OFF_AR_EPOCH : COMM_OFF_AG_EPOCH))) + 1u;
+    r.off = ar ? comm_ar_slot_off(p.comm, (int)(r.epoch & 1u), p.comm.rank) : comm_ag_off(p.comm, p.comm.rank);
+    return r;
+}
+template <bool GRP>
+__device__ __forceinline__ void mv_store(const MatvecParams& p, const RpState& rp, int64_t idx, double v) {
+    if (GRP || p.rp_mode == RP_NONE) {
+        store_out_d(p.y, p.y_dtype, idx, v);
+    } else if (p.rp_mode == RP_ALLREDUCE) {
+        for (int r = 0; r < p.comm.world; r++) reinterpret_cast<double*>(p.comm.peers[r] + rp.off)[idx] = v;
+    } else {
+        const float f = (float)v;
+        for (int r = 0; r < p.comm.world; r++) reinterpret_cast<float*>(p.comm.peers[r] + rp.off)[idx] = f;
+    }
+}
+// row-parallel shards each add their partial sum: the bias must enter the total once (rank 0)
+__device__ __forceinline__ bool mv_use_bias(const MatvecParams& p) { return p.bias && (p.rp_mode != RP_ALLREDUCE || p.comm.rank == 0); }
+constexpr int MV_BAR_DONE = 5;  // consumers + fix-up warp: every output store of this CTA is issued
+
 template <class F, int MB, bool PRO, bool GRP>
 __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -229,6 +259,18 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 if (!PRO) bulk_g2s(st + wbytes, chunk_x(j), xbytes, &full[s]);
                 if (++s == nst) { s = 0; ph ^= 1u; }
             }
+            // every chunk of this launch is requested: keep HBM busy with the successor's first chunks (L2 prefetch)
+            if (!GRP && p.next_pf > 0) {
+                for (int64_t ng = g; ng < p.next_G; ng += G) {
+                    const int64_t a0 = sk_begin(ng, p.next_C, p.next_G), a1 = sk_begin(ng + 1, p.next_C, p.next_G);
+                    const SkPlan np_ = sk_plan(a0, a1, p.next_KC);
+                    const int n = (int)(a1 - a0) < p.next_pf ? (int)(a1 - a0) : p.next_pf;
+                    for (int j = 0; j < n; j++)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.next_w + sk_chunk_at(np_, a0, j) * (int64_t)p.next_chunk_bytes),
+                                     "r"(p.next_chunk_bytes)
+                                     : "memory");
+                }
+            }
         }
         return;
     }
@@ -236,8 +278,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         // ===================== fix-up warp: arrival atomics + ordered reduction of split tiles =====================
         // Runs beside the consumers (they only bar.arrive), so neither the math nor the TMA stream ever waits
         // for an atomic round trip.  Split tiles are processed first, so this finishes long before the CTA does.
-        if (sp.nH == 0 && sp.nT == 0) return;
+        const bool rp_on = !GRP && p.rp_mode != RP_NONE;
+        if (sp.nH == 0 && sp.nT == 0) {
+            if (rp_on) named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
+            return;
+        }
         pdl_wait();
+        const RpState rp = rp_begin(p);
         // arrival bookkeeping is computed before the barriers: only the atomic round trip is on the critical path
         int64_t tqs[2] = {sp.tH, sp.tT};
         int gfs[2], ncs[2], sgfs[2];
@@ -292,17 +339,19 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
                     const int64_t n = tql * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) store_out_d(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, sv[e] + (p.bias ? (double)p.bias[n] : 0.0));
+                    if (n < p.N && m < p.M) mv_store<GRP>(p, rp, ybase + (int64_t)m * p.ldy + n, sv[e] + (mv_use_bias(p) ? (double)p.bias[n] : 0.0));
                 }
             }
             if (lane == 0) p.ws_cnt[tq] = 0u;
             if (p.trace && lane == 0) p.trace[g * 8 + 7] = globaltimer_ns();
         }
+        if (rp_on) named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
         return;
     }
 
     // ===================== consumers =====================
     pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
+    const RpState rp = rp_begin(p);
     const int g4 = lane >> 3, i = lane & 7;
     const FmtMeta meta{p.gpc};
     // f64 accumulators: every term is an exact product of an f32 scale and an integer partial, so the sum is
@@ -403,10 +452,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
                     const int64_t n = tl * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
                     if (n < p.N) {
-                        const double bv = p.bias ? (double)p.bias[n] : 0.0;
+                        const double bv = mv_use_bias(p) ? (double)p.bias[n] : 0.0;
 #pragma unroll
                         for (int m = 0; m < MB; m++)
-                            if (m < p.M) store_out_d(p.y, p.y_dtype, ybase + (int64_t)m * p.ldy + n, acc[s4][m] + bv);
+                            if (m < p.M) mv_store<GRP>(p, rp, ybase + (int64_t)m * p.ldy + n, acc[s4][m] + bv);
                     }
                 }
             }
@@ -435,6 +484,26 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; kcur = 0; }
         else { seg_left = KC; t++; }
 
+    }
+    if (!GRP && p.rp_mode != RP_NONE) {
+        // ---- fused exchange, producer side: this CTA's peer stores are all issued; the last CTA of the launch publishes ----
+        named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
+        if (tid == 0) {
+            uint8_t* mine = p.comm.peers[p.comm.rank];
+            const bool ar = p.rp_mode == RP_ALLREDUCE;
+            unsigned int* done = reinterpret_cast<unsigned int*>(mine + (ar ? COMM_OFF_AR_DONE : COMM_OFF_AG_DONE));
+            __threadfence_system();  // the CTA's peer stores (ordered before this thread by the barrier) are performed system-wide
+            unsigned int old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
+            if (old == (unsigned int)(G - 1)) {
+                *done = 0u;  // next launch (ordered after this one by the stream)
+                const int par = ar ? (int)(rp.epoch & 1u) : 0;
+                const int foff = ar ? COMM_OFF_AR_FLAGS : COMM_OFF_AG_FLAGS;
+                for (int r = 0; r < p.comm.world; r++)
+                    st_release_sys(reinterpret_cast<unsigned int*>(p.comm.peers[r] + foff) + par * COMM_MAX_WORLD + p.comm.rank, rp.epoch);
+                *reinterpret_cast<unsigned int*>(mine + (ar ? COMM_OFF_AR_EPOCH : COMM_OFF_AG_EPOCH)) = rp.epoch;
+            }
+        }
     }
     if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }

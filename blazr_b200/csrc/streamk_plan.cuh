@@ -43,5 +43,11 @@ __device__ __forceinline__ SkPlan sk_plan(int64_t c0, int64_t c1, int64_t KC) {
     return s;
 }
 
+// index (in the tile-major chunk array) of the j-th chunk a CTA with range [c0, ...) and plan sp processes
+__device__ __forceinline__ int64_t sk_chunk_at(const SkPlan& sp, int64_t c0, int j) {
+    if (j < sp.nH) return c0 + j;
+    if (j < sp.nH + sp.nT) return c0 + sp.nH + sp.nF + (j - sp.nH);
+    return c0 + sp.nH + (j - sp.nH - sp.nT);
+}
 
 }  // namespace b200q

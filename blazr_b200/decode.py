@@ -243,10 +243,18 @@ class Decoder:
             act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
             self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
         import os as _os
+        # streaming-order hints: every decode matvec prefetches the head of the next projection's weights into L2 while its own
+        # tail drains (qkv -> o -> gate|up -> down -> next layer ... -> lm_head -> layer 0 of the next token)
+        if not self.wide and _os.environ.get("B200Q_CHAIN", "1") != "0":
+            order = [ln.w for lay in self.layers for key in ("qkv", "o", "gu", "down") for ln in lay[key]] + [ln.w for ln in self.head]
+            for a, b in zip(order, order[1:] + order[:1]):
+                if a is not b:
+                    a.set_next(b)
         self.fused = _os.environ.get("B200Q_FUSED", "0") != "0" and not self.wide   # add+norm+quant fused into the matvec prologue
         self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0" and not self.wide  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
+        self._host_pos = 0
         # EXPERIMENTAL (B200Q_DSTEP=1, single GPU, M <= 4): persistent op-list kernel, 3 launches per layer instead of 8
         self.programs = None
         self.step_program = None
@@ -259,8 +267,9 @@ class Decoder:
         # to torch.distributed (NCCL) all-reduce of f32 partials for comparison
         self.comm = None
         if tp_world > 1 and _os.environ.get("B200Q_TP_NCCL", "0") == "0":
-            self.comm = ops.PeerComm(tp_rank, tp_world, M * H, dev, group)
-            self.part64 = torch.zeros((M, H), dtype=torch.float64, device=dev)
+            assert not self.fused and not self.fused_swiglu and self.programs is None and self.step_program is None
+            self.vs = tp.vocab_shard_rows(cfg.vocab, tp_world)
+            self.comm = ops.PeerComm(tp_rank, tp_world, M * H, dev, group, gather_elems=M * self.vs)
 
     # ---- weights ------------------------------------------------------------------------------------
     def _fused(self, layer: int, parts, K: int, host: Optional[HostModel], kslice=None) -> List[_Linear]:
@@ -421,24 +430,48 @@ class Decoder:
                                          C.c_void_p(out.data_ptr() + out.element_size() * ln.col0), C.c_int32(dt), C.c_int64(out.stride(0)),
                                          C.c_void_p(ln.ws.data_ptr()), C.c_size_t(ln.ws.numel()), st))
 
-    def _rowpar(self, lins: List[_Linear], xq: torch.Tensor, out: torch.Tensor):
-        """row-parallel projection + all-reduce(sum) into out (f32).  TP: the matvec leaves its exact f64 partial sums,
-        the one-shot NVLink all-reduce sums them in rank order and rounds once (bit-identical to the 1-GPU output)."""
-        if self.world == 1:
-            self._matvec(lins, xq, out)
-        elif self.comm is not None:
-            self._matvec(lins, xq, self.part64)
-            self.comm.allreduce_f64(self.part64, out)
-        else:
-            self._matvec(lins, xq, out)
+    def _rowpar(self, lins: List[_Linear], xq: torch.Tensor, out: torch.Tensor) -> bool:
+        """row-parallel projection (o_proj / down_proj).  Returns True when the result is left IN FLIGHT in the exchange
+        buffers: the matvec pushed its exact f64 row sums to every rank (fused exchange, csrc/comm_dev.cuh) and the next
+        add+norm kernel is the consumer that sums them in rank order (bit-identical to the 1-GPU output).  Otherwise `out`
+        (f32) holds the projection (1 GPU) or its NCCL all-reduce (B200Q_TP_NCCL=1, comparison only)."""
+        if self.comm is not None:
+            assert len(lins) == 1
+            self.comm.matmul_q8_rowpar(lins[0].w, xq, self.M, self.cfg.hidden, lins[0].ws)
+            return True
+        self._matvec(lins, xq, out)
+        if self.world > 1:
             torch.distributed.all_reduce(out, group=self.group)
+        return False
 
     def _allreduce(self, t: torch.Tensor):
         if self.world > 1:
             torch.distributed.all_reduce(t, group=self.group)
 
+    def _advance(self):
+        """host-side mirror of the device position counter: every step (eager or replayed) passes through here, so a
+        sequence can never run past the KV cache / RoPE table (the kernel guards too: b200q_decode_error)"""
+        if self._host_pos >= self.max_ctx:
+            raise RuntimeError(f"decode step at position {self._host_pos} exceeds max_ctx={self.max_ctx}: the KV cache is full "
+                               "(build the Decoder with a larger max_ctx)")
+        self._host_pos += 1
+
+    def replay(self):
+        """one captured decode step (CUDA-graph replay), position-checked on the host"""
+        self._advance()
+        self.graph.replay()
+
+    def check_device_errors(self):
+        """raises if a kernel refused an out-of-range position since the last check (synchronises the device)"""
+        flags = C.c_int32(0)
+        ops._check(ops.lib().b200q_decode_error(C.byref(flags)))
+        if flags.value:
+            raise RuntimeError(f"decode kernels reported error flags 0x{flags.value:x} (bit 0: position outside [0, max_ctx))")
+
     def step(self):
         """ids (device) -> next ids (device); positions advance on the device: graph-replayable."""
+        if not torch.cuda.is_current_stream_capturing():
+            self._advance()
         if self.step_program is not None:
             return self.step_program.launch()
         if self.programs is not None:
@@ -449,12 +482,16 @@ class Decoder:
         ops._check(L.b200q_embed(P(self.embed), P(self.ids), C.c_int64(cfg.hidden), C.c_int64(M), P(self.h), st))
         hin, hout = self.h, self.h2
         delta = None
+        in_flight = False  # TP: the projection ahead left its partial sums in the exchange buffers (see _rowpar)
 
         def norm(w):
             nonlocal hin, hout
-            ops._check(L.b200q_add_rmsnorm_quant(P(hin), P(delta) if delta is not None else None, P(hout), P(w), C.c_float(cfg.eps),
-                                                 C.c_int64(cfg.hidden), C.c_int64(M), None if self.wide else P(self.xq_h),
-                                                 P(self.xq_h) if self.wide else None, st))
+            if in_flight:
+                self.comm.allreduce_add_rmsnorm_quant(hin, hout, w, cfg.eps, cfg.hidden, M, xq=self.xq_h)
+            else:
+                ops._check(L.b200q_add_rmsnorm_quant(P(hin), P(delta) if delta is not None else None, P(hout), P(w), C.c_float(cfg.eps),
+                                                     C.c_int64(cfg.hidden), C.c_int64(M), None if self.wide else P(self.xq_h),
+                                                     P(self.xq_h) if self.wide else None, st))
             hin, hout = hout, hin
 
         def matvec_norm(lins, w, out):
@@ -476,7 +513,7 @@ class Decoder:
             ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
                                            C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
                                            None if self.wide else P(self.xq_attn), P(self.xq_attn) if self.wide else None, st))
-            self._rowpar(lay["o"], self.xq_attn, self.delta)
+            in_flight = self._rowpar(lay["o"], self.xq_attn, self.delta)
             delta = self.delta
             if fused:
                 matvec_norm(lay["gu"], lay["mlp_norm"], self.gu)
@@ -495,12 +532,18 @@ class Decoder:
                     ops._check(L.b200q_swiglu_f32(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
                 else:
                     ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
-                self._rowpar(lay["down"], self.xq_ff, self.delta2)
+                in_flight = self._rowpar(lay["down"], self.xq_ff, self.delta2)
                 delta = self.delta2
         if fused:
             matvec_norm(self.head, self.final_norm, self.logits_local)
         else:
             norm(self.final_norm)
+        if self.comm is not None:
+            # vocabulary-parallel lm_head: logits go straight into every rank's gather area, the arg-max is the consumer
+            assert len(self.head) == 1
+            self.comm.matmul_q8_gather(self.head[0].w, self.xq_h, M, self.vs, self.head[0].ws)
+            self.comm.argmax_gathered(self.vs, M, self.ids, self.pos)
+            return
         if not fused:
             self._matvec(self.head, self.xq_h, self.logits_local)
         if self.world > 1:
@@ -511,6 +554,15 @@ class Decoder:
         else:
             ops._check(L.b200q_argmax(P(self.logits), C.c_int64(self.logits.shape[1]), C.c_int64(M), P(self.ids), P(self.pos), st))
 
+    def full_logits(self) -> torch.Tensor:
+        """[M, vocab] f32 logits of the last step on this rank (TP: assembled from the gather area / the all-gather)"""
+        if self.comm is not None:
+            g = self.comm.gathered()[:, :self.M * self.vs].reshape(self.world, self.M, self.vs)
+            return g.permute(1, 0, 2).reshape(self.M, -1)[:, :self.cfg.vocab].contiguous()
+        if self.world > 1:
+            return self._full_logits
+        return self.logits
+
     def launches_per_step(self) -> int:
         if getattr(self, "_launches", None):
             return self._launches  # counted by the library during the un-captured warm-up step
@@ -519,8 +571,6 @@ class Decoder:
         n = 1 + glue + len(self.head) + 1  # embed, (final norm), head, argmax
         for lay in self.layers:
             n += 2 * glue + len(lay["qkv"]) + 1 + len(lay["o"]) + len(lay["gu"]) + sw + len(lay["down"])
-            if self.comm is not None:
-                n += 2  # the two one-shot all-reduce kernels (ours; NCCL kernels are not counted)
         return n
 
     def capture(self):
@@ -528,6 +578,8 @@ class Decoder:
         n0 = ops.launch_count()
         self.step()  # un-captured warm-up forward (cuda_graphs.rs:104)
         self._launches = ops.launch_count() - n0
+        self.pos.sub_(1)      # the warm-up forward is not part of any sequence: undo its position advance
+        self._host_pos -= 1
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(self.dev)
@@ -542,15 +594,18 @@ class Decoder:
     def reset(self, first_ids):
         self.ids.copy_(torch.as_tensor(first_ids, dtype=torch.int64, device=self.dev).reshape(self.M))
         self.pos.zero_()
+        self._host_pos = 0
 
     def generate(self, prompt: np.ndarray, n_new: int, use_graph: bool = True) -> np.ndarray:
         """prompt: int64 [M, S].  Greedy: feeds the prompt token by token (decode steps), then n_new tokens."""
         prompt = np.asarray(prompt, dtype=np.int64).reshape(self.M, -1)
         S = prompt.shape[1]
+        if S + n_new - 1 > self.max_ctx:
+            raise ValueError(f"prompt ({S}) + new tokens ({n_new}) - 1 = {S + n_new - 1} positions exceed max_ctx={self.max_ctx}")
         if use_graph and self.graph is None:
             self.capture()
         self.reset(prompt[:, 0])
-        run = (lambda: self.graph.replay()) if use_graph else self.step
+        run = self.replay if use_graph else self.step
         out = []
         for s_ in range(S + n_new - 1):
             run()
@@ -559,4 +614,5 @@ class Decoder:
             else:
                 out.append(self.ids.clone())
         torch.cuda.synchronize(self.dev)
+        self.check_device_errors()
         return torch.stack(out, dim=1).cpu().numpy()

@@ -243,7 +243,8 @@ def get_gguf_info(path: str) -> GgufInfo:
 
 def config_from_gguf_metadata(g: Gguf):
     """ModelConfig from the file's metadata: same keys and defaults as reference gguf.rs:101-200
-    (hidden 4096, heads 32, kv heads = heads, eps 1e-5, rope base 10000, head_dim = key_length or hidden / heads)."""
+    (heads 32, kv heads = heads, eps 1e-5, rope base 10000, head_dim = key_length or hidden / heads; a missing
+    embedding_length or block_count is an error, gguf.rs:120-130)."""
     from .decode import ModelConfig
 
     m = g.metadata()
@@ -257,7 +258,9 @@ def config_from_gguf_metadata(g: Gguf):
             vocab = g.tensor_info("token_embd.weight").shape[1]
         else:
             raise GgufError("cannot determine the vocabulary size")
-    hidden = m.get_u32(f"{arch}.embedding_length") or 4096
+    hidden = m.get_u32(f"{arch}.embedding_length")
+    if hidden is None:
+        raise GgufError(f"GGUF missing {arch}.embedding_length")  # reference gguf.rs:122 (an error there too, no default)
     layers = m.get_u32(f"{arch}.block_count")
     if layers is None:
         raise GgufError(f"missing {arch}.block_count")
@@ -268,6 +271,9 @@ def config_from_gguf_metadata(g: Gguf):
     eps = m.get_f32(f"{arch}.attention.layer_norm_rms_epsilon") or 1e-5
     theta = m.get_f32(f"{arch}.rope.freq_base") or 10000.0
     return ModelConfig(m.get("general.name", arch), hidden, layers, heads, kv, hd, ffn, vocab, theta, eps)
+
+
+SUPPORTED_DECODER_ARCHS = frozenset({"llama", "mistral"})
 
 
 def _to_f32(g: Gguf, name: str) -> np.ndarray:
@@ -284,13 +290,28 @@ def _to_f32(g: Gguf, name: str) -> np.ndarray:
 
 def host_model_from_gguf(g: Gguf, client=None):
     """HostModel (the structure Decoder and the oracle consume) whose projections are zero-copy views of the file.
-    Supported: Llama-family dense models (llama / mistral / qwen2-style naming) with Q4_K / Q6_K / Q8_0 projections;
-    anything else raises (no silent fallback).  A quantized token_embd is dequantized on the GPU through `client`."""
+    Supported: dense Llama-family decoders -- general.architecture "llama" or "mistral" (llama.cpp stores their Q / K
+    rows permuted for the adjacent-pair RoPE the attention operator applies) -- with any ggml weight type the library
+    has a kernel for.  Anything else raises (no silent fallback): other architectures (qwen2 / phi3 / gemma use the
+    NEOX rotate-half RoPE and projection biases), and files holding tensors this decoder would silently ignore
+    (*.bias, rope_freqs, stacked *_exps expert tensors -- the latter go through moe_mlp_from_gguf).
+    A quantized token_embd is dequantized on the GPU through `client`."""
     from . import synth
     from .decode import HostLinear, HostModel
 
+    arch = g.metadata().architecture() or "llama"
+    if arch not in SUPPORTED_DECODER_ARCHS:
+        raise GgufError(f"general.architecture '{arch}' is not supported by the decode harness (supported: {sorted(SUPPORTED_DECODER_ARCHS)}): "
+                        "its RoPE layout / biases differ from the Llama family")
     cfg = config_from_gguf_metadata(g)
     names = set(g.tensor_names())
+    consumed = {"token_embd.weight", "output_norm.weight", "output.weight"}
+    for i in range(cfg.n_layers):
+        consumed |= {f"blk.{i}.{n}.weight" for n in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down", "attn_norm", "ffn_norm")}
+    extra = sorted(names - consumed)
+    if extra:
+        raise GgufError(f"the file holds {len(extra)} tensor(s) the dense Llama-family decoder does not consume (e.g. {extra[:4]}): "
+                        "refusing to load and silently drop them")
     by_type = {v: k for k, v in synth.GGML.items()}
 
     def linear(name: str, N: int, K: int) -> HostLinear:

@@ -51,12 +51,13 @@ class WeightInfo(C.Structure):
 EXPORTS = [
     "b200q_version", "b200q_last_error", "b200q_device_count", "b200q_weight_from_ggml", "b200q_weight_from_ggml_shard",
     "b200q_weight_from_awq", "b200q_weight_from_gptq", "b200q_weight_from_awq_shard", "b200q_weight_free", "b200q_weight_info",
-    "b200q_weight_set_bias", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
+    "b200q_weight_set_bias", "b200q_weight_set_next", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
-    "b200q_argmax", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
+    "b200q_argmax", "b200q_decode_error", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
     "b200q_swiglu_f32", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq", "b200q_program_add_attn", "b200q_program_add_argmax", "b200q_program_add_embed",
-    "b200q_program_finalize", "b200q_program_launch", "b200q_program_free", "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free",
+    "b200q_program_finalize", "b200q_program_launch", "b200q_program_free", "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free", "b200q_comm_gather_ptr",
+    "b200q_matmul_q8_rowpar", "b200q_allreduce_add_rmsnorm_quant", "b200q_allreduce_finish", "b200q_matmul_q8_gather", "b200q_argmax_gathered", "b200q_allreduce",
     "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
 ]
 
@@ -79,6 +80,7 @@ def lib() -> C.CDLL:
         L.b200q_bank_workspace_bytes.restype = C.c_size_t
         L.b200q_bank_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
         L.b200q_bank_get.restype = C.c_void_p
+        L.b200q_weight_set_next.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -160,11 +162,18 @@ class QuantWeight:
             self._ws[M] = ws
         return ws
 
+    def set_next(self, nxt: Optional["QuantWeight"]):
+        """streaming-order hint (include/b200q.h b200q_weight_set_next): the decode matvec on this weight prefetches the head
+        of `nxt` into L2.  A reference to `nxt` is kept so the hint can never dangle."""
+        _check(lib().b200q_weight_set_next(self._h, nxt.handle if nxt is not None else None))
+        self._next = nxt
+
     def free(self):
         if self._h is not None:
             lib().b200q_weight_free(self._h)
             self._h = None
             self._ws = {}
+            self._next = None
 
     def __del__(self):
         try:
@@ -450,14 +459,24 @@ class Program:
             self._h = None
 
 
-class PeerComm:
-    """One-shot NVLink all-reduce context (include/b200q.h b200q_comm_*).  `group` is only used once, to all-gather
-    the CUDA IPC handles; the data path never touches NCCL."""
+class _DevView:
+    """zero-copy torch view of library-owned device memory (CUDA array interface)"""
 
-    def __init__(self, rank: int, world: int, max_elems: int, device: torch.device, group=None):
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerComm:
+    """Tensor-parallel exchange context over NVLink peer memory (include/b200q.h b200q_comm_*).  `group` is only used once,
+    to all-gather the CUDA IPC handles; the data path never touches NCCL.  The exchange is fused into the kernels on both
+    sides of it: matmul_q8_rowpar (producer) -> allreduce_add_rmsnorm_quant / allreduce_finish (consumer), and
+    matmul_q8_gather -> argmax_gathered for the vocabulary-parallel lm_head."""
+
+    def __init__(self, rank: int, world: int, max_elems: int, device: torch.device, group=None, gather_elems: int = 0):
         self.rank, self.world, self.device = rank, world, device
         h = C.c_void_p()
-        _check(lib().b200q_comm_create(C.c_int32(rank), C.c_int32(world), C.c_int64(max_elems), C.c_int32(device.index or 0), C.byref(h)))
+        _check(lib().b200q_comm_create(C.c_int32(rank), C.c_int32(world), C.c_int64(max_elems), C.c_int64(gather_elems), C.c_int32(device.index or 0),
+                                       C.byref(h)))
         self._h = h
         mine = (C.c_uint8 * 64)()
         _check(lib().b200q_comm_handle(self._h, mine))
@@ -472,10 +491,45 @@ class PeerComm:
             import torch.distributed as dist
             dist.barrier(group=group)
 
+    @property
+    def handle(self):
+        return self._h
+
+    def allreduce(self, src: torch.Tensor, dst: torch.Tensor):
+        """stand-alone one-shot all-reduce(sum): dst (f32) = sum over ranks of src (f32 or f64), f64 sum in rank order"""
+        assert src.dtype in (torch.float64, torch.float32) and dst.dtype == torch.float32 and src.numel() == dst.numel()
+        _check(lib().b200q_allreduce(self._h, C.c_void_p(src.data_ptr()), C.c_int32(F64 if src.dtype == torch.float64 else F32),
+                                     C.c_void_p(dst.data_ptr()), C.c_int64(src.numel()), _stream_ptr(self.device)))
+
     def allreduce_f64(self, src: torch.Tensor, dst: torch.Tensor):
-        assert src.dtype == torch.float64 and dst.dtype == torch.float32 and src.numel() == dst.numel()
-        _check(lib().b200q_allreduce_f64(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int64(src.numel()),
-                                         _stream_ptr(self.device)))
+        self.allreduce(src, dst)
+
+    def matmul_q8_rowpar(self, w: "QuantWeight", xq: torch.Tensor, M: int, ld: int, workspace: torch.Tensor):
+        """row-parallel matvec whose exact f64 row sums [M, ld] go straight into every rank's exchange slot"""
+        _check(lib().b200q_matmul_q8_rowpar(w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(M), self._h, C.c_int64(ld), C.c_void_p(workspace.data_ptr()),
+                                            C.c_size_t(workspace.numel()), _stream_ptr(self.device)))
+
+    def allreduce_finish(self, dst: torch.Tensor):
+        _check(lib().b200q_allreduce_finish(self._h, C.c_void_p(dst.data_ptr()), C.c_int64(dst.numel()), _stream_ptr(self.device)))
+
+    def allreduce_add_rmsnorm_quant(self, h_in, h_out, norm_w, eps: float, H: int, M: int, xq=None, xnorm=None):
+        _check(lib().b200q_allreduce_add_rmsnorm_quant(self._h, C.c_void_p(h_in.data_ptr()), C.c_void_p(h_out.data_ptr()), C.c_void_p(norm_w.data_ptr()),
+                                                       C.c_float(eps), C.c_int64(H), C.c_int64(M), C.c_void_p(xq.data_ptr()) if xq is not None else None,
+                                                       C.c_void_p(xnorm.data_ptr()) if xnorm is not None else None, _stream_ptr(self.device)))
+
+    def matmul_q8_gather(self, w: "QuantWeight", xq: torch.Tensor, M: int, ld: int, workspace: torch.Tensor):
+        _check(lib().b200q_matmul_q8_gather(w.handle, C.c_void_p(xq.data_ptr()), C.c_int64(M), self._h, C.c_int64(ld), C.c_void_p(workspace.data_ptr()),
+                                            C.c_size_t(workspace.numel()), _stream_ptr(self.device)))
+
+    def argmax_gathered(self, ld: int, M: int, out_ids: torch.Tensor, pos_inc: Optional[torch.Tensor]):
+        _check(lib().b200q_argmax_gathered(self._h, C.c_int64(ld), C.c_int64(M), C.c_void_p(out_ids.data_ptr()),
+                                           C.c_void_p(pos_inc.data_ptr()) if pos_inc is not None else None, _stream_ptr(self.device)))
+
+    def gathered(self) -> torch.Tensor:
+        """f32 [world, elems_per_rank] view of this rank's gather area (region r = what rank r stored)"""
+        ptr, n = C.c_void_p(), C.c_int64()
+        _check(lib().b200q_comm_gather_ptr(self._h, C.byref(ptr), C.byref(n)))
+        return torch.as_tensor(_DevView(ptr.value, (self.world, n.value), "<f4"), device=self.device)
 
     def free(self):
         if self._h is not None:

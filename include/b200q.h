@@ -119,6 +119,12 @@ int32_t b200q_weight_free(b200q_weight* w);
 int32_t b200q_weight_info(const b200q_weight* w, b200q_weight_info_t* info);
 /* optional f32 bias [N] (device copy is made) added in every matmul epilogue */
 int32_t b200q_weight_set_bias(b200q_weight* w, const float* bias, int32_t src_on_device, void* stream);
+/* Streaming-order hint (performance only; results never depend on it): `next` is the weight the caller will run through
+ * b200q_matmul_q8 right after `w` (the model's projection order: qkv -> o -> gate|up -> down -> next layer's qkv ...).
+ * A decode matvec on `w` then prefetches the first chunks of `next` into L2 once its own weight stream is fully requested,
+ * so HBM keeps streaming across the kernel boundary and the glue operators in between.  `next` is not owned: clear the
+ * hint (next = NULL) before freeing it.  The one mutable field of a handle; set it before the handle is shared. */
+int32_t b200q_weight_set_next(b200q_weight* w, const b200q_weight* next);
 
 /* reference src/engine/tensor_parallel.rs:61-67 */
 int32_t b200q_shard_range(int64_t total, int64_t rank, int64_t world, int64_t* start, int64_t* end);
@@ -178,17 +184,38 @@ int32_t b200q_moe_matmul_q8(const b200q_bank* b, const int32_t* sel_dev, int64_t
                             int64_t x_slot_div, void* y, int32_t y_dtype, int64_t y_slot_stride, void* workspace,
                             size_t workspace_bytes, void* stream);
 
-/* ---- tensor-parallel exchange over NVLink peer memory (replaces the NCCL all-reduce blazr's TP would issue after
- * the row-parallel o_proj / down_proj, reference src/engine/tensor_parallel.rs:125-160).
- * One process per GPU: create on every rank, all-gather the 64-byte IPC handles, connect.  b200q_allreduce_f64 sums
- * the ranks' f64 partial sums (b200q_matmul_q8 with y_dtype = B200Q_F64) in rank order and rounds once to f32, so the
- * result is identical on every rank and equal to the 1-GPU output.  Graph-capturable, no host sync. */
+/* ---- tensor-parallel exchange over NVLink peer memory, FUSED into the kernels on both sides of it (replaces the NCCL
+ * all-reduce blazr's TP issues after the row-parallel o_proj / down_proj, reference src/engine/tensor_parallel.rs:125-163;
+ * SURVEY.md sections 5 and 8b/8e).  One process per GPU: create on every rank, all-gather the 64-byte IPC handles, connect.
+ *   producer  b200q_matmul_q8_rowpar : the row-parallel matvec stores its exact f64 row sums [M, ld] straight into a slot of
+ *             every rank's buffer (peer stores from the kernel's flush paths); its last CTA raises the epoch flags.
+ *   consumer  b200q_allreduce_add_rmsnorm_quant : polls the flags in local memory, sums the `world` slots in rank order in
+ *             f64, rounds once (identical bits on every rank and equal to the 1-GPU output), adds the residual, RMS-norms and
+ *             quantises -- the reduced vector never exists in HBM and the exchange costs no launch of its own.
+ *             b200q_allreduce_finish is the stand-alone consumer (reduced f32 vector) for other callers.
+ *   lm_head   b200q_matmul_q8_gather (column-parallel over the vocabulary) stores f32 logits [M, ld] into region `rank` of
+ *             every rank's gather area; b200q_argmax_gathered consumes them (vocabulary id = rank * ld + column).
+ *   b200q_allreduce : stand-alone one-shot push all-reduce of a device vector (expert-parallel partial outputs).
+ * Every producer call must be followed by exactly one consumer call on every rank before the next producer call of the same
+ * kind.  All entry points are graph-capturable (epochs live in device memory). */
 typedef struct b200q_comm b200q_comm;
-int32_t b200q_comm_create(int32_t rank, int32_t world, int64_t max_elems, int32_t device, b200q_comm** out);
+/* max_elems: doubles per all-reduce slot (>= M * hidden); gather_elems: floats per rank in the gather area (>= M * ld, 0 = none) */
+int32_t b200q_comm_create(int32_t rank, int32_t world, int64_t max_elems, int64_t gather_elems, int32_t device, b200q_comm** out);
 int32_t b200q_comm_handle(const b200q_comm* c, void* out64);
 int32_t b200q_comm_connect(b200q_comm* c, const void* handles /* world x 64 bytes, rank order */);
-int32_t b200q_allreduce_f64(b200q_comm* c, const double* src, float* dst, int64_t n, void* stream);
 int32_t b200q_comm_free(b200q_comm* c);
+/* device pointer of this rank's gather area: f32 [world][elems_per_rank] */
+int32_t b200q_comm_gather_ptr(const b200q_comm* c, void** ptr, int64_t* elems_per_rank);
+int32_t b200q_matmul_q8_rowpar(const b200q_weight* w, const void* xq, int64_t M, b200q_comm* c, int64_t ld, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int32_t b200q_allreduce_add_rmsnorm_quant(b200q_comm* c, const float* h_in, float* h_out, const float* norm_w, float eps, int64_t H, int64_t M,
+                                          void* xq, float* xnorm, void* stream);
+int32_t b200q_allreduce_finish(b200q_comm* c, float* dst, int64_t n, void* stream);
+int32_t b200q_matmul_q8_gather(const b200q_weight* w, const void* xq, int64_t M, b200q_comm* c, int64_t ld, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int32_t b200q_argmax_gathered(b200q_comm* c, int64_t ld, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream);
+int32_t b200q_allreduce(b200q_comm* c, const void* src, int32_t src_dtype /* B200Q_F32 | B200Q_F64 */, float* dst, int64_t n, void* stream);
+int32_t b200q_allreduce_f64(b200q_comm* c, const double* src, float* dst, int64_t n, void* stream); /* = b200q_allreduce(.., B200Q_F64, ..) */
 
 /* Decode matmuls with a fused activation producer (M <= 4): the consumer warps build the quantised activation in
  * shared memory while the first weight chunks are in flight, so no separate norm / SwiGLU kernel runs.
@@ -219,7 +246,8 @@ int32_t b200q_int_partials(const b200q_weight* w, const void* xq, int64_t M, int
  * (b200q_act_bytes layout) that the following b200q_matmul_q8 consumes, so no separate quantise pass runs.
  * Reference call sites: src/engine/cuda_graphs.rs:101-130 (captured forward + argmax_to_buf). */
 /* h_out[M,H] = h_in (+ delta, nullable); xq = quant(rmsnorm(h_out) * w); xnorm (nullable) receives the f32 normalised
- * row.  h_in and h_out must differ when delta != NULL (the operator runs H/256 CTAs wide and re-reads the row). */
+ * row.  h_in and h_out must differ when delta != NULL.  H <= 8192 runs as one thread-block cluster per row (the row is read
+ * once, the sum of squares is combined through distributed shared memory); larger H runs H/256 CTAs wide. */
 int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_out, const float* w, float eps, int64_t H, int64_t M,
                                 void* xq, float* xnorm, void* stream);
 /* xq = quant(silu(gate) * up) for gate_up[M, 2F] (gate first) */
@@ -232,6 +260,10 @@ int32_t b200q_swiglu_f32(const float* gate_up, int64_t F, int64_t M, float* act,
  * qkv[M,(nh+2nkv)*hd] f32; caches [M][max_ctx][nkv][hd] f32; attn_out (nullable) receives the f32 result */
 int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table, int32_t n_heads,
                           int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq, float* attn_out, void* stream);
+/* A position pos[m] outside [0, max_ctx) makes b200q_attn_decode write nothing and raise a sticky per-device error
+ * word instead of indexing past the KV cache.  b200q_decode_error reads and clears it for the current device
+ * (synchronises the device: not capturable; call it after a generate loop).  bit 0 = position out of range. */
+int32_t b200q_decode_error(int32_t* out_flags);
 /* greedy token: argmax over V, lowest index wins ties; pos_inc (nullable) is incremented per row (graph replay) */
 int32_t b200q_argmax(const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream);
 /* h[m,:] = f16 table[ids[m],:] */

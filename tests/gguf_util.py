@@ -3,7 +3,7 @@ converter's own writer) from a HostModel, so the tests drive our parser with a f
 import numpy as np
 
 
-def write_gguf(path, hm, arch="llama", tie_output=False):
+def write_gguf(path, hm, arch="llama", tie_output=False, extra_tensors=None):
     import gguf
     from gguf import GGMLQuantizationType as QT
 
@@ -36,6 +36,8 @@ def write_gguf(path, hm, arch="llama", tie_output=False):
     w.add_tensor("output_norm.weight", hm.final_norm.astype(np.float32))
     if not tie_output:
         lin("output.weight", hm.lm_head)
+    for name, arr in (extra_tensors or {}).items():
+        w.add_tensor(name, arr)
     w.write_header_to_file()
     w.write_kv_data_to_file()
     w.write_tensors_to_file()

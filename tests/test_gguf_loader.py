@@ -114,3 +114,27 @@ def test_stacked_expert_tensors(tmp_path):
         assert np.array_equal(gu_b[:ffn], gate[e]) and np.array_equal(gu_b[ffn:], up[e]) and np.array_equal(dn_b, down[e])
     assert gguf_loader.get_gguf_info(path).is_moe
     assert gguf_loader.hf_name("blk.0.ffn_gate_exps.weight") == "model.layers.0.mlp.experts.gate_proj.weight"
+
+
+def test_unsupported_architecture_and_stray_tensors_raise(tmp_path):
+    """No silent fallback: a qwen2-tagged file (NEOX RoPE, q/k/v biases) is refused, a llama file that carries tensors the dense
+    decoder would drop (a bias here) is refused, and a missing embedding_length is an error as in reference gguf.rs:120-123."""
+    hm = decode.build_host_model(decode.PRESETS["tiny"], "Q8_0", seed=5)
+    p1 = str(tmp_path / "qwen.gguf")
+    write_gguf(p1, hm, arch="qwen2")
+    with pytest.raises(gguf_loader.GgufError, match="architecture 'qwen2'"):
+        gguf_loader.host_model_from_gguf(gguf_loader.Gguf.open(p1))
+    p2 = str(tmp_path / "bias.gguf")
+    write_gguf(p2, hm, extra_tensors={"blk.0.attn_q.bias": np.zeros(hm.cfg.n_heads * hm.cfg.head_dim, dtype=np.float32)})
+    with pytest.raises(gguf_loader.GgufError, match="does not consume"):
+        gguf_loader.host_model_from_gguf(gguf_loader.Gguf.open(p2))
+    p3 = str(tmp_path / "mistral.gguf")
+    write_gguf(p3, hm, arch="mistral")
+    assert len(gguf_loader.host_model_from_gguf(gguf_loader.Gguf.open(p3)).layers) == hm.cfg.n_layers
+    w = gguf.GGUFWriter(str(tmp_path / "noemb.gguf"), "llama")
+    w.add_block_count(2)
+    w.add_vocab_size(100)
+    w.add_tensor("dummy", np.zeros(4, dtype=np.float32))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    with pytest.raises(gguf_loader.GgufError, match="embedding_length"):
+        gguf_loader.config_from_gguf_metadata(gguf_loader.Gguf.open(str(tmp_path / "noemb.gguf")))

@@ -40,10 +40,13 @@ def make_weight(client, fmt, N, K, seed):
     raise ValueError(fmt)
 
 
-def bench_case(client, fmt, N, K, M, reps=20, path=ops.PATH_AUTO, split=True):
+def bench_case(client, fmt, N, K, M, reps=20, path=ops.PATH_AUTO, split=True, chain=False):
     w0 = make_weight(client, fmt, N, K, seed=1)
     copies = int(min(96, max(2, -(-L2_DEFEAT_BYTES // w0.canonical_bytes))))
     ws = [w0] + [make_weight(client, fmt, N, K, seed=1) for _ in range(copies - 1)]  # same bytes, distinct buffers
+    if chain:  # successor hints between the rotating copies (what a model's projection order gives the decode path)
+        for a, b in zip(ws, ws[1:] + ws[:1]):
+            a.set_next(b)
     x = torch.from_numpy(synth.random_act(M, K)).cuda()
     y = torch.empty((M, N), device="cuda", dtype=torch.float32)
     wss = [w.workspace(M) for w in ws]
@@ -93,6 +96,7 @@ def main():
     ap.add_argument("--fmts", default="Q4_K,Q6_K,Q8_0,AWQ")
     ap.add_argument("--ms", default="1")
     ap.add_argument("--path", type=int, default=0)
+    ap.add_argument("--chain", action="store_true", help="set b200q_weight_set_next between consecutive launches")
     args = ap.parse_args()
     client = ops.B200Client(0)
     shapes = [(4096, 4096), (14336, 4096), (4096, 14336), (28672, 4096)]
@@ -102,7 +106,7 @@ def main():
     for fmt in args.fmts.split(","):
         for (N, K) in shapes:
             for M in [int(m) for m in args.ms.split(",")]:
-                r = bench_case(client, fmt, N, K, M, path=args.path)
+                r = bench_case(client, fmt, N, K, M, path=args.path, chain=args.chain)
                 out.append(r)
                 print(f"{fmt:5s} N={N:6d} K={K:6d} M={M:4d}  {r['us']:9.2f} us  {r['GBs']:8.1f} GB/s  {100 * r['frac_hbm']:5.1f}% HBM  "
                       f"{r['TFLOPs']:7.2f} TF/s  copies={r['copies']}", flush=True)

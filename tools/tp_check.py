@@ -16,7 +16,7 @@ for scheme in (("Q4_K_M", "Q8_0", "AWQ") if world <= 2 else ("Q4_K_M",)):
     dec = decode.Decoder(client, cfg, scheme, batch=1, max_ctx=96, host=hm, tp_rank=rank, tp_world=world)
     prompt = np.asarray([[3, 1, 4, 1, 5, 9, 2, 6]])
     got = dec.generate(prompt, 48, use_graph=True)[0]
-    logits_tp = dec._full_logits[0].cpu().numpy()
+    logits_tp = dec.full_logits()[0].cpu().numpy()
     if rank == 0:
         ref_dec = decode.Decoder(client, cfg, scheme, batch=1, max_ctx=96, host=hm)
         ref = ref_dec.generate(prompt, 48, use_graph=True)[0]
@@ -24,7 +24,7 @@ for scheme in (("Q4_K_M", "Q8_0", "AWQ") if world <= 2 else ("Q4_K_M",)):
         same = bool(np.array_equal(got, ref))
         err = float(np.abs(logits_tp - lref).max() / np.abs(lref).max())
         bits = float((logits_tp.view(np.uint32) != lref.view(np.uint32)).mean())
-        print(f"tp{world} {scheme}: exchange={'peer-memory one-shot' if dec.comm is not None else 'NCCL'} logits differing in any bit: {bits:.2e}", flush=True)
+        print(f"tp{world} {scheme}: exchange={'fused peer-memory (matvec push -> norm / arg-max consumer)' if dec.comm is not None else 'NCCL'} logits differing in any bit: {bits:.2e}", flush=True)
         print(f"tp{world} {scheme}: greedy stream equal={same} first mismatch={int(np.nonzero(got != ref)[0][0]) if not same else -1} last-step logits rel err={err:.2e}", flush=True)
         ok = ok and (same or err < 1e-4)
     dist.barrier()

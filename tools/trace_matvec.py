@@ -7,10 +7,13 @@ from tools.kbench import make_weight
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--fmt", default="Q6_K"); ap.add_argument("--N", type=int, default=14336); ap.add_argument("--K", type=int, default=4096)
-ap.add_argument("--n", type=int, default=8)
+ap.add_argument("--n", type=int, default=8); ap.add_argument("--chain", action="store_true")
 a = ap.parse_args()
 client = ops.B200Client(0)
 ws = [make_weight(client, a.fmt, a.N, a.K, seed=1) for _ in range(a.n)]
+if a.chain:
+    for w0_, w1_ in zip(ws, ws[1:] + ws[:1]):
+        w0_.set_next(w1_)
 x = torch.from_numpy(synth.random_act(1, a.K)).cuda()
 xq = client.quantize_act(x)
 y = torch.empty((1, a.N), device="cuda")
