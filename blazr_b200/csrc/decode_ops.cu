@@ -165,12 +165,16 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
         for (int r = 0; r < ncta; r++) tot += *cluster.map_shared_rank(&cta_part, r);  // CTA order: identical on every CTA
         if (lane == 0) s_inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)H), eps)));
     }
-    cluster.sync();  // (also keeps every CTA's shared memory alive until its peers have read it)
-    if (!active) return;
-    h_out[(size_t)m * H + k] = v;
-    const float x = __fmul_rn(__fmul_rn(v, s_inv), wk);
-    if (xnorm) xnorm[(size_t)m * H + k] = x;
-    if (xq) quant_store_record(x, xq + ((size_t)(k / CHUNK_K) * M + m) * ACT_REC_BYTES, k % CHUNK_K);
+    // a CTA's shared memory must stay alive until its peers have read cta_part: arrive now, wait only before exiting
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();  // s_inv
+    if (active) {
+        h_out[(size_t)m * H + k] = v;
+        const float x = __fmul_rn(__fmul_rn(v, s_inv), wk);
+        if (xnorm) xnorm[(size_t)m * H + k] = x;
+        if (xq) quant_store_record(x, xq + ((size_t)(k / CHUNK_K) * M + m) * ACT_REC_BYTES, k % CHUNK_K);
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,8 +504,12 @@ int32_t b200q_add_rmsnorm_quant(const float* h_in, const float* delta, float* h_
                                 float* xnorm, void* stream) {
     if (!h_in || !h_out || !w || (!xq && !xnorm) || H <= 0 || H % CHUNK_K || M <= 0) return B200Q_ERR_INVALID_ARG;
     if (delta && h_in == h_out) return B200Q_ERR_INVALID_ARG;  // CTAs re-read the whole input row: no in-place update
-    static const bool old_kernel = [] { const char* e_ = getenv("B200Q_NORM_OLD"); return e_ && atoi(e_) != 0; }();
-    if (H <= 8 * NORMC_NT && !old_kernel) {  // one cluster per row: the row is read once
+    // measured (round 2, Mistral-7B / Llama-3.2-1B steps): without an exchange to consume, the H/256-CTA kernel (every CTA
+    // re-reads the L2-resident row) beats the cluster form by ~1.3 us per call -- two cluster barriers cost more than the
+    // redundant reads.  The cluster kernel is the tensor-parallel consumer (reading `world` slots per CTA would not scale);
+    // B200Q_NORM_CLUSTER=1 forces it here for A/B runs.
+    static const bool use_cluster = [] { const char* e_ = getenv("B200Q_NORM_CLUSTER"); return e_ && atoi(e_) != 0; }();
+    if (H <= 8 * NORMC_NT && use_cluster) {
         cudaError_t e = launch_norm_cluster(CommDev{}, h_in, delta, h_out, w, eps, H, M, xq, xnorm, (cudaStream_t)stream);
         return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
     }

@@ -142,9 +142,9 @@ __device__ __forceinline__ RpState rp_begin(const MatvecParams& p) {
     r.off = ar ? comm_ar_slot_off(p.comm, (int)(r.epoch & 1u), p.comm.rank) : comm_ag_off(p.comm, p.comm.rank);
     return r;
 }
-template <bool GRP>
+template <bool RP>
 __device__ __forceinline__ void mv_store(const MatvecParams& p, const RpState& rp, int64_t idx, double v) {
-    if (GRP || p.rp_mode == RP_NONE) {
+    if constexpr (!RP) {
         store_out_d(p.y, p.y_dtype, idx, v);
     } else if (p.rp_mode == RP_ALLREDUCE) {
         for (int r = 0; r < p.comm.world; r++) reinterpret_cast<double*>(p.comm.peers[r] + rp.off)[idx] = v;
@@ -154,10 +154,12 @@ __device__ __forceinline__ void mv_store(const MatvecParams& p, const RpState& r
     }
 }
 // row-parallel shards each add their partial sum: the bias must enter the total once (rank 0)
-__device__ __forceinline__ bool mv_use_bias(const MatvecParams& p) { return p.bias && (p.rp_mode != RP_ALLREDUCE || p.comm.rank == 0); }
+template <bool RP>
+__device__ __forceinline__ bool mv_use_bias(const MatvecParams& p) { return p.bias && (!RP || p.rp_mode != RP_ALLREDUCE || p.comm.rank == 0); }
 constexpr int MV_BAR_DONE = 5;  // consumers + fix-up warp: every output store of this CTA is issued
 
-template <class F, int MB, bool PRO, bool GRP>
+// RP (compile time, like GRP: the plain matvec carries none of it): fused tensor-parallel exchange, producer side
+template <class F, int MB, bool PRO, bool GRP, bool RP>
 __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -278,13 +280,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         // ===================== fix-up warp: arrival atomics + ordered reduction of split tiles =====================
         // Runs beside the consumers (they only bar.arrive), so neither the math nor the TMA stream ever waits
         // for an atomic round trip.  Split tiles are processed first, so this finishes long before the CTA does.
-        const bool rp_on = !GRP && p.rp_mode != RP_NONE;
+        constexpr bool rp_on = RP;
         if (sp.nH == 0 && sp.nT == 0) {
             if (rp_on) named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
             return;
         }
         pdl_wait();
-        const RpState rp = rp_begin(p);
+        RpState rp{0u, 0};
+        if constexpr (RP) rp = rp_begin(p);
         // arrival bookkeeping is computed before the barriers: only the atomic round trip is on the critical path
         int64_t tqs[2] = {sp.tH, sp.tT};
         int gfs[2], ncs[2], sgfs[2];
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
                     const int64_t n = tql * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) mv_store<GRP>(p, rp, ybase + (int64_t)m * p.ldy + n, sv[e] + (mv_use_bias(p) ? (double)p.bias[n] : 0.0));
+                    if (n < p.N && m < p.M) mv_store<RP>(p, rp, ybase + (int64_t)m * p.ldy + n, sv[e] + (mv_use_bias<RP>(p) ? (double)p.bias[n] : 0.0));
                 }
             }
             if (lane == 0) p.ws_cnt[tq] = 0u;
@@ -351,7 +354,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
 
     // ===================== consumers =====================
     pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
-    const RpState rp = rp_begin(p);
+    RpState rp{0u, 0};
+    if constexpr (RP) rp = rp_begin(p);
     const int g4 = lane >> 3, i = lane & 7;
     const FmtMeta meta{p.gpc};
     // f64 accumulators: every term is an exact product of an f32 scale and an integer partial, so the sum is
@@ -452,10 +456,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
                     const int64_t n = tl * TILE_ROWS + MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
                     if (n < p.N) {
-                        const double bv = mv_use_bias(p) ? (double)p.bias[n] : 0.0;
+                        const double bv = mv_use_bias<RP>(p) ? (double)p.bias[n] : 0.0;
 #pragma unroll
                         for (int m = 0; m < MB; m++)
-                            if (m < p.M) mv_store<GRP>(p, rp, ybase + (int64_t)m * p.ldy + n, acc[s4][m] + bv);
+                            if (m < p.M) mv_store<RP>(p, rp, ybase + (int64_t)m * p.ldy + n, acc[s4][m] + bv);
                     }
                 }
             }
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         else { seg_left = KC; t++; }
 
     }
-    if (!GRP && p.rp_mode != RP_NONE) {
+    if constexpr (RP) {
         // ---- fused exchange, producer side: this CTA's peer stores are all issued; the last CTA of the launch publishes ----
         named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
         if (tid == 0) {
@@ -508,13 +512,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }
 
-template <class F, int MB, bool PRO, bool GRP>
+template <class F, int MB, bool PRO, bool GRP, bool RP = false>
 static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStream_t st) {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -528,7 +532,7 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP>, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP, RP>, p);
     if (le != cudaSuccess) return le;
     count_launch();
     return cudaGetLastError();
@@ -536,7 +540,16 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
 
 template <class F>
 static cudaError_t launch_f(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
-    if (p.w_table) return mb == 1 && !p.pro ? launch_t<F, 1, false, true>(p, grid, smem, st) : cudaErrorInvalidValue;
+    if (p.w_table) return mb == 1 && !p.pro && !p.rp_mode ? launch_t<F, 1, false, true>(p, grid, smem, st) : cudaErrorInvalidValue;
+    if (p.rp_mode != RP_NONE) {  // fused tensor-parallel exchange (row-parallel o / down, vocabulary-parallel lm_head)
+        if (p.pro) return cudaErrorInvalidValue;
+        switch (mb) {
+            case 1: return launch_t<F, 1, false, false, true>(p, grid, smem, st);
+            case 2: return launch_t<F, 2, false, false, true>(p, grid, smem, st);
+            case 4: return launch_t<F, 4, false, false, true>(p, grid, smem, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (mb) {
         case 1: return p.pro ? launch_t<F, 1, true, false>(p, grid, smem, st) : launch_t<F, 1, false, false>(p, grid, smem, st);
         case 2: return p.pro ? launch_t<F, 2, true, false>(p, grid, smem, st) : launch_t<F, 2, false, false>(p, grid, smem, st);

@@ -245,7 +245,7 @@ class Decoder:
         import os as _os
         # streaming-order hints: every decode matvec prefetches the head of the next projection's weights into L2 while its own
         # tail drains (qkv -> o -> gate|up -> down -> next layer ... -> lm_head -> layer 0 of the next token)
-        if not self.wide and _os.environ.get("B200Q_CHAIN", "1") != "0":
+        if not self.wide and _os.environ.get("B200Q_CHAIN", "0") != "0":  # measured neutral on whole steps (round 2): opt-in
             order = [ln.w for lay in self.layers for key in ("qkv", "o", "gu", "down") for ln in lay[key]] + [ln.w for ln in self.head]
             for a, b in zip(order, order[1:] + order[:1]):
                 if a is not b:
