@@ -492,6 +492,19 @@ int32_t b200q_moe_matmul_q8(const b200q_bank* b, const int32_t* sel_dev, int64_t
     return B200Q_OK;
 }
 
+/* grouped gate|up with the fused SwiGLU epilogue: slot s writes the quantised activation row s of xq_out (n_slots rows) */
+int32_t b200q_moe_matmul_q8_swiglu(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const void* xq, int64_t x_rows, int64_t x_slot_div,
+                                   void* xq_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!b || !sel_dev || !xq || !xq_out || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+    if (n_slots < 1 || n_slots > 65536) return fail(B200Q_ERR_INVALID_ARG, "n_slots out of range");
+    if (x_slot_div < 1 || x_rows < 1 || (n_slots + x_slot_div - 1) / x_slot_div > x_rows) return fail(B200Q_ERR_INVALID_ARG, "activation rows do not cover the slots");
+    if (b->proto.N % 128) return fail(B200Q_ERR_UNSUPPORTED, "SwiGLU epilogue needs N = 2 F with F %% 64 == 0 (got N = %lld)", (long long)b->proto.N);
+    if (workspace_bytes < b200q_bank_workspace_bytes(b, n_slots)) return fail(B200Q_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, b200q_bank_workspace_bytes(b, n_slots));
+    CUDA_TRY(launch_matvec_grouped(b, sel_dev, n_slots, (const uint8_t*)xq, x_rows, x_slot_div, nullptr, B200Q_F32, b->proto.N, (uint8_t*)workspace,
+                                   (cudaStream_t)stream, xq_out));
+    return B200Q_OK;
+}
+
 int32_t b200q_matmul_path(const b200q_weight* w, int32_t path, const void* x, int32_t x_dtype, int64_t M, int64_t ldx, void* y,
                           int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
     if (!w || !x || !y || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
@@ -561,10 +574,50 @@ int32_t b200q_matmul_norm(const b200q_weight* w, const float* h_in, const float*
     int32_t rc = fused_common(w, M, y, y_dtype, ldy, workspace, workspace_bytes);
     if (rc) return rc;
     if (!h_in || !norm_w) return fail(B200Q_ERR_INVALID_ARG, "null h_in / norm_w");
-    if (w->K > 8192) return fail(B200Q_ERR_UNSUPPORTED, "fused norm prologue supports K <= 8192");
+    {
+        const int64_t ept = w->K / 512;  // elements per consumer thread: the lane-parallel prologue needs a power of two <= 16
+        if (w->K % 512 || ept > 16 || (ept & (ept - 1))) return fail(B200Q_ERR_UNSUPPORTED, "fused norm prologue supports K in {512, 1024, 2048, 4096, 8192} (got %lld)", (long long)w->K);
+    }
     if (delta && h_out == h_in) return fail(B200Q_ERR_INVALID_ARG, "h_out must not alias h_in when delta is given");
     FusedPrologue fp{1, h_in, delta, h_out, norm_w, eps, nullptr};
     CUDA_TRY(launch_matvec(w, nullptr, M, y, y_dtype, ldy, (uint8_t*)workspace, (cudaStream_t)stream, &fp));
+    return B200Q_OK;
+}
+
+/* ---- fused SwiGLU epilogue: w = gate|up with rows interleaved per 128-row tile (b200q_gate_up_row); writes the quantised
+ * activation records of the following down projection instead of y ---- */
+static int32_t swiglu_weight_ok(const b200q_weight* w) {
+    if (w->N % 128) return fail(B200Q_ERR_UNSUPPORTED, "SwiGLU epilogue needs N = 2 F with F %% 64 == 0 (got N = %lld)", (long long)w->N);
+    return B200Q_OK;
+}
+int64_t b200q_gate_up_row(int64_t F, int64_t r) {
+    /* source row, in the concatenated [gate (F rows); up (F rows)] matrix, of row r of the interleaved weight */
+    const int64_t t = r / 128, rr = r % 128, w_ = rr / 8, s_ = (rr % 8) / 4, g_ = rr % 4;
+    return (s_ ? F : 0) + 64 * t + 4 * w_ + g_;
+}
+int32_t b200q_matmul_q8_swiglu(const b200q_weight* w, const void* xq, int64_t M, void* xq_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!w || !xq || !xq_out || !workspace) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+    if (M < 1 || M > 4) return fail(B200Q_ERR_UNSUPPORTED, "matmul_q8_swiglu handles M in [1,4] (got %lld)", (long long)M);
+    if (int32_t rc = swiglu_weight_ok(w)) return rc;
+    if (workspace_bytes < align256(matvec_ws_bytes(w, M))) return fail(B200Q_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, align256(matvec_ws_bytes(w, M)));
+    CUDA_TRY(launch_matvec(w, (const uint8_t*)xq, M, nullptr, B200Q_F32, w->N, (uint8_t*)workspace, (cudaStream_t)stream, nullptr, nullptr, xq_out));
+    return B200Q_OK;
+}
+int32_t b200q_matmul_norm_swiglu(const b200q_weight* w, const float* h_in, const float* delta, float* h_out, const float* norm_w, float eps, int64_t M,
+                                 void* xq_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!xq_out) return fail(B200Q_ERR_INVALID_ARG, "null xq_out");
+    float dummy;
+    int32_t rc = fused_common(w, M, &dummy, B200Q_F32, w ? w->N : 0, workspace, workspace_bytes);
+    if (rc) return rc;
+    if ((rc = swiglu_weight_ok(w))) return rc;
+    if (!h_in || !norm_w) return fail(B200Q_ERR_INVALID_ARG, "null h_in / norm_w");
+    {
+        const int64_t ept = w->K / 512;
+        if (w->K % 512 || ept > 16 || (ept & (ept - 1))) return fail(B200Q_ERR_UNSUPPORTED, "fused norm prologue supports K in {512, 1024, 2048, 4096, 8192} (got %lld)", (long long)w->K);
+    }
+    if (delta && h_out == h_in) return fail(B200Q_ERR_INVALID_ARG, "h_out must not alias h_in when delta is given");
+    FusedPrologue fp{1, h_in, delta, h_out, norm_w, eps, nullptr};
+    CUDA_TRY(launch_matvec(w, nullptr, M, nullptr, B200Q_F32, w->N, (uint8_t*)workspace, (cudaStream_t)stream, &fp, nullptr, xq_out));
     return B200Q_OK;
 }
 

@@ -10,7 +10,7 @@ using namespace b200q;
 // Replays one launch with G CTAs over T tiles x KC chunks.  Returns 0 when every invariant holds, else a code:
 //  1 chunk not covered exactly once            2 a CTA's segments do not add up to its range
 //  3 the consumer walk flushes a wrong tile    4 fix-up contributor range / count / slot mismatch
-//  5 a tile flagged "full" is not owned by one CTA
+//  5 a tile flagged "full" is not owned by one CTA      6 the 32-bit plan differs from the 64-bit plan
 extern "C" int streamk_check(int64_t T, int64_t KC, int64_t G_in, int64_t* n_split_tiles, int64_t* max_contrib) {
     const int64_t C = T * KC;
     int64_t G = G_in > C ? C : G_in;   // matvec_plan clamps the grid to the chunk count
@@ -22,6 +22,13 @@ extern "C" int streamk_check(int64_t T, int64_t KC, int64_t G_in, int64_t* n_spl
         const int64_t c0 = sk_begin(g, C, G), c1 = sk_begin(g + 1, C, G);
         if (c1 <= c0) return 2;
         const SkPlan sp = sk_plan(c0, c1, KC);
+        if ((C + 1) * G < (1ll << 32)) {  // the kernel's 32-bit fast path must agree with the 64-bit definition
+            const uint32_t a0 = sk_begin32((uint32_t)g, (uint32_t)C, (uint32_t)G), a1 = sk_begin32((uint32_t)g + 1, (uint32_t)C, (uint32_t)G);
+            const SkPlan s32 = sk_plan32(a0, a1, (uint32_t)KC);
+            if (a0 != c0 || a1 != c1 || s32.nH != sp.nH || s32.nT != sp.nT || s32.nF != sp.nF || s32.kcH != sp.kcH || s32.tH != sp.tH || s32.tT != sp.tT ||
+                s32.tF != sp.tF)
+                return 6;
+        }
         const int n = (int)(c1 - c0);
         if (sp.nH + sp.nT + sp.nF != n || sp.nH < 0 || sp.nT < 0 || sp.nF < 0 || sp.nF % KC != 0) return 2;
         // producer order (matvec_impl.cuh chunk_vc): head, tail, full

@@ -66,10 +66,10 @@ void set_matvec_trace(long long* dev_buf);
 cudaError_t launch_l2_prefetch(const b200q_weight* w, int64_t M, int64_t max_bytes, cudaStream_t st);
 struct RemoteOut;  // fused TP exchange target (comm_dev.cuh: mode + CommDev)
 cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
-                          const FusedPrologue* fp = nullptr, const RemoteOut* ro = nullptr);
+                          const FusedPrologue* fp = nullptr, const RemoteOut* ro = nullptr, void* swiglu_xq_out = nullptr);
 size_t matvec_grouped_ws_bytes(const b200q_bank* b, int64_t n_slots);
 cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const uint8_t* xq, int64_t x_rows, int64_t x_slot_div,
-                                  void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st);
+                                  void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st, void* swiglu_xq_out = nullptr);
 
 // ---- comm.cu ----
 struct CommDev;

@@ -61,7 +61,7 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int 
     // the placement, doubled-up CTAs run at half speed and the launch takes 2x); cross-launch overlap is done
     // with the L2 prefetch kernel instead
     int budget_kb = 150;
-    if (const char* e = getenv("B200Q_MV_SMEM_KB")) { int v = atoi(e); if (v >= 64 && v <= 224) budget_kb = v; }
+    if (const char* e = getenv("B200Q_MV_SMEM_KB")) { int v = atoi(e); if (v >= 64 && v <= 214) budget_kb = v; }
     int budget = budget_kb * 1024 - MV_HDR_BYTES - xhat;
     int nst = budget / stage;
     if (nst > MV_MAX_STAGES) nst = MV_MAX_STAGES;
@@ -89,7 +89,7 @@ size_t matvec_ws_bytes(const b200q_weight* w, int64_t M) {
 }
 
 cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, void* y, int y_dtype, int64_t ldy, uint8_t* ws, cudaStream_t st,
-                          const FusedPrologue* fp, const RemoteOut* ro) {
+                          const FusedPrologue* fp, const RemoteOut* ro, void* swiglu_xq_out) {
     MatvecPlan plan;
     const int pro = fp ? fp->mode : 0;
     cudaError_t e = matvec_plan(w, M, &plan, pro);
@@ -128,6 +128,10 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.y_slot_stride = 0;
     p.trace = g_trace ? g_trace + (size_t)(g_trace_launch++) * 148 * 8 : nullptr;
     p.debug_flags = 0;
+    p.xq_out = (uint8_t*)swiglu_xq_out;
+    p.epi_F = (int)(w->N / 2);
+    p.epi_rows = (int)M;
+    p.plan32 = ((p.C + 1) * (int64_t)plan.grid < (1ll << 32)) ? 1 : 0;
     p.rp_mode = ro ? ro->mode : RP_NONE;
     if (ro) p.comm = ro->comm;
     else p.comm = CommDev{};
@@ -170,7 +174,7 @@ size_t matvec_grouped_ws_bytes(const b200q_bank* b, int64_t n_slots) {
 }
 
 cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const uint8_t* xq, int64_t x_rows, int64_t x_slot_div,
-                                  void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st) {
+                                  void* y, int y_dtype, int64_t y_slot_stride, uint8_t* ws, cudaStream_t st, void* swiglu_xq_out) {
     b200q_weight v = b->proto;  // virtual weight: the selected experts' tiles back to back
     v.T = b->proto.T * n_slots;
     MatvecPlan plan;
@@ -203,6 +207,10 @@ cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, i
     p.y_slot_stride = y_slot_stride;
     p.next_w = nullptr;
     p.next_pf = 0;
+    p.xq_out = (uint8_t*)swiglu_xq_out;
+    p.epi_F = (int)(b->proto.N / 2);
+    p.epi_rows = (int)n_slots;
+    p.plan32 = ((p.C + 1) * (int64_t)plan.grid < (1ll << 32)) ? 1 : 0;
     return launch_family(v.family, p, 1, plan.grid, plan.smem_bytes, st);
 }
 

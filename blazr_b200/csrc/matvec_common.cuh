@@ -55,6 +55,13 @@ struct MatvecParams {
     // the slot / region = m * ldy + n.  The last CTA of the launch raises this rank's epoch flag at every peer.
     int rp_mode;
     CommDev comm;
+    // fused SwiGLU epilogue (OUT_SWIGLU): w is a gate|up weight whose rows are interleaved per 128-row tile (tile t, row
+    // 8 w + 4 s + g  <->  (s == 0 ? gate : up)[64 t + 4 w + g]); every finished tile yields 64 values silu(gate) * up =
+    // two 32-blocks, quantised straight into the next matvec's activation records xq_out[kc][epi_rows][320].
+    uint8_t* xq_out;
+    int epi_F;      // rows of gate (= rows of up) = N / 2
+    int epi_rows;   // record rows per k-chunk: M (plain) or n_slots (grouped)
+    int plan32;     // (C + 1) * G < 2^32: the stream-K plan is computed with 32-bit divisions
     const uint8_t* const* w_table;
     const int32_t* sel;
     int tpw;              // tiles per weight

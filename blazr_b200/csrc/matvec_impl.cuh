@@ -42,77 +42,144 @@ __device__ __forceinline__ void quant_block_to_record(float v, uint8_t* rec, int
     }
 }
 
+// static norm weights of this thread's elements (plain loads: never written during the step), fetched ahead of the wait
+template <int EPT>
+__device__ __forceinline__ void load_nw(const float* __restrict__ w, int tid, float (&nw)[EPT]) {
+    if constexpr (EPT >= 4) {
+#pragma unroll
+        for (int q = 0; q < EPT / 4; q++) {
+            const float4 f = reinterpret_cast<const float4*>(w + EPT * tid)[q];
+            nw[4 * q] = f.x; nw[4 * q + 1] = f.y; nw[4 * q + 2] = f.z; nw[4 * q + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; j++) nw[j] = w[EPT * tid + j];
+    }
+}
+__device__ __forceinline__ void pdl_wait_again() { pdl_wait(); }  // PRO kernels: the consumers' dependency wait, after their static loads
+
+// ---- norm prologue, lane-parallel form: thread t of the 512 consumer threads owns the EPT = K / 512 consecutive elements
+// [EPT t, EPT t + EPT); a 32-block is 32 / EPT adjacent lanes, so every lane belongs to exactly ONE block: the two IEEE
+// divides of the quantiser run once per lane (not once per block per warp), the block maximum / sums are 1-5 shuffles.
+// Everything that does not depend on the preceding kernel (norm weights) is loaded by the caller ahead of
+// griddepcontrol.wait.  One L2 round trip (h_in, delta) + one 512-thread barrier for the sum of squares.
+template <int EPT>
+__device__ __forceinline__ void load_ept(const float* __restrict__ p, float (&v)[EPT]) {
+    if constexpr (EPT >= 4) {
+#pragma unroll
+        for (int q = 0; q < EPT / 4; q++) {
+            const float4 f = __ldcg(reinterpret_cast<const float4*>(p) + q);  // written by the kernel ahead: L2
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+    } else if constexpr (EPT == 2) {
+        const float2 f = __ldcg(reinterpret_cast<const float2*>(p));
+        v[0] = f.x; v[1] = f.y;
+    } else {
+        v[0] = __ldcg(p);
+    }
+}
+template <int EPT>
+__device__ __forceinline__ void store_ept(float* __restrict__ p, const float (&v)[EPT]) {
+    if constexpr (EPT >= 4) {
+#pragma unroll
+        for (int q = 0; q < EPT / 4; q++) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else if constexpr (EPT == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+        p[0] = v[0];
+    }
+}
+
+template <int MB, int EPT>
+__device__ __forceinline__ void norm_prologue(const MatvecParams& p, uint8_t* xhat, const float (&nw)[EPT], int tid, int warp, int lane, bool writer,
+                                              double* red /*[16]*/) {
+    constexpr int NT = MV_CONSUMER_WARPS * 32;
+    constexpr int LPB = 32 / EPT;  // lanes per 32-block
+    const int K = EPT * NT;
+    const int e0 = EPT * tid;
+    for (int m = 0; m < p.M; m++) {
+        float v[EPT];
+        load_ept<EPT>(p.h_in + (size_t)m * K + e0, v);
+        if (p.delta) {
+            float dl[EPT];
+            load_ept<EPT>(p.delta + (size_t)m * K + e0, dl);
+#pragma unroll
+            for (int j = 0; j < EPT; j++) v[j] = __fadd_rn(v[j], dl[j]);
+        }
+        if (writer && p.h_out) store_ept<EPT>(p.h_out + (size_t)m * K + e0, v);
+        double ss = 0.0;
+#pragma unroll
+        for (int j = 0; j < EPT; j++) ss = fma((double)v[j], (double)v[j], ss);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        named_bar_sync(4, NT);
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < MV_CONSUMER_WARPS; i++) tot += red[i];
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)K), p.eps)));
+        float x[EPT];
+        float amax = 0.0f;
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            x[j] = __fmul_rn(__fmul_rn(v[j], inv), nw[j]);
+            amax = fmaxf(amax, fabsf(x[j]));
+        }
+#pragma unroll
+        for (int o = LPB / 2; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float d = __fdiv_rn(amax, 127.0f);
+        const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+        int s = 0;
+        uint8_t* rec = xhat + ((size_t)(e0 / CHUNK_K) * p.M + m) * ACT_REC_BYTES;
+        const int off = e0 % CHUNK_K;
+        if constexpr (EPT >= 4) {
+#pragma unroll
+            for (int q4 = 0; q4 < EPT / 4; q4++) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int q = (int)roundf(__fmul_rn(x[4 * q4 + c], id));
+                    s += q;
+                    wv |= ((uint32_t)q & 0xFFu) << (8 * c);
+                }
+                *reinterpret_cast<uint32_t*>(rec + off + 4 * q4) = wv;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EPT; j++) {
+                const int q = (int)roundf(__fmul_rn(x[j], id));
+                s += q;
+                rec[off + j] = (uint8_t)(int8_t)q;
+            }
+        }
+        // sums of the two 16-element halves of the block: lanes [0, LPB/2) of the block hold the first half
+        if constexpr (LPB >= 4) {
+#pragma unroll
+            for (int o = LPB / 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        }
+        int s_lo, s_hi;
+        if constexpr (LPB >= 2) {
+            const int other = __shfl_xor_sync(0xffffffffu, s, LPB / 2);
+            s_lo = s; s_hi = other;  // valid on the block's first lane
+        } else {  // EPT == 32 is not instantiated
+            s_lo = s; s_hi = 0;
+        }
+        if ((lane % LPB) == 0) {
+            const int blk = off / 32;
+            reinterpret_cast<float*>(rec + 256)[blk] = d;
+            reinterpret_cast<uint32_t*>(rec + 288)[blk] = ((uint32_t)s_lo & 0xFFFFu) | ((uint32_t)s_hi << 16);
+        }
+        if (m + 1 < p.M) named_bar_sync(4, NT);  // red[] is reused by the next row
+    }
+    named_bar_sync(4, NT);  // records visible to every consumer warp
+}
+
 template <int MB>
 __device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* xhat, int tid, int warp, int lane, bool writer) {
     constexpr int NT = MV_CONSUMER_WARPS * 32;
     const int K = (int)p.KC * CHUNK_K;
     const int nblk = K / 32;
-    if (p.pro == 1) {
-        // ---- h = h_in (+ delta); xhat = quant(rmsnorm(h) * w) ----
-        // warp w owns the 32-blocks w, w+16, ...; every element is loaded once (all loads in flight together),
-        // kept in registers for the sum of squares and then normalised + quantised from registers.
-        constexpr int VMAX = 16;  // K <= 8192
-        __shared__ double red[MB][MV_CONSUMER_WARPS];
-        __shared__ float s_inv[MB];
-        const int nv = (nblk + MV_CONSUMER_WARPS - 1) / MV_CONSUMER_WARPS;
-        float v[MB][VMAX];
-#pragma unroll
-        for (int m = 0; m < MB; m++) {
-            if (m >= p.M) break;
-            const float* hr = p.h_in + (size_t)m * K;
-            const float* dr = p.delta ? p.delta + (size_t)m * K : nullptr;
-#pragma unroll
-            for (int j = 0; j < VMAX; j++) {
-                const int b = warp + j * MV_CONSUMER_WARPS;
-                v[m][j] = (j < nv && b < nblk) ? hr[b * 32 + lane] : 0.0f;
-            }
-            if (dr) {
-#pragma unroll
-                for (int j = 0; j < VMAX; j++) {
-                    const int b = warp + j * MV_CONSUMER_WARPS;
-                    if (j < nv && b < nblk) v[m][j] = __fadd_rn(v[m][j], dr[b * 32 + lane]);
-                }
-            }
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < VMAX; j += 2) {
-                s0 = fma((double)v[m][j], (double)v[m][j], s0);
-                s1 = fma((double)v[m][j + 1], (double)v[m][j + 1], s1);
-            }
-            double ss = s0 + s1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if (lane == 0) red[m][warp] = ss;
-            if (writer && p.h_out) {
-#pragma unroll
-                for (int j = 0; j < VMAX; j++) {
-                    const int b = warp + j * MV_CONSUMER_WARPS;
-                    if (j < nv && b < nblk) p.h_out[(size_t)m * K + b * 32 + lane] = v[m][j];
-                }
-            }
-        }
-        named_bar_sync(4, NT);
-        if (tid < p.M) {
-            double tot = 0.0;
-#pragma unroll
-            for (int i = 0; i < MV_CONSUMER_WARPS; i++) tot += red[tid][i];
-            s_inv[tid] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)K), p.eps)));
-        }
-        named_bar_sync(4, NT);
-#pragma unroll
-        for (int m = 0; m < MB; m++) {
-            if (m >= p.M) break;
-            const float inv = s_inv[m];
-#pragma unroll
-            for (int j = 0; j < VMAX; j++) {
-                const int b = warp + j * MV_CONSUMER_WARPS;
-                if (j < nv && b < nblk) {
-                    const float x = __fmul_rn(__fmul_rn(v[m][j], inv), p.norm_w[b * 32 + lane]);
-                    quant_block_to_record(x, xhat + ((size_t)(b >> 3) * p.M + m) * ACT_REC_BYTES, b & 7, lane);
-                }
-            }
-        }
-    } else {
+    {
         // ---- xhat = quant(silu(gate) * up), gate_up[M, 2K] ----
         for (int m = 0; m < p.M; m++) {
             const float* gr = p.gate_up + (size_t)m * 2 * K;
@@ -157,10 +224,32 @@ __device__ __forceinline__ void mv_store(const MatvecParams& p, const RpState& r
 template <bool RP>
 __device__ __forceinline__ bool mv_use_bias(const MatvecParams& p) { return p.bias && (!RP || p.rp_mode != RP_ALLREDUCE || p.comm.rank == 0); }
 constexpr int MV_BAR_DONE = 5;  // consumers + fix-up warp: every output store of this CTA is issued
+constexpr int MV_BAR_EPI_FULL = 6;   // (+ buffer 0/1) consumers -> fix-up warp: a finished tile sits in s_y[buffer]
+constexpr int MV_BAR_EPI_FREE = 8;   // (+ buffer 0/1) fix-up warp -> consumers: s_y[buffer] may be overwritten
 
-// RP (compile time, like GRP: the plain matvec carries none of it): fused tensor-parallel exchange, producer side
-template <class F, int MB, bool PRO, bool GRP, bool RP>
+// where finished row sums go (compile time, like GRP: the plain matvec carries none of the other forms)
+enum { OUT_PLAIN = 0, OUT_REMOTE = 1 /* fused tensor-parallel exchange */, OUT_SWIGLU = 2 /* fused SwiGLU + quantise epilogue */ };
+
+// ---- OUT_SWIGLU: one finished 128-row tile (64 gate / 64 up rows interleaved, f32 in shared memory) -> 64 activations
+// silu(gate) * up -> two quantised 32-blocks of the next matvec's records.  Executed by the fix-up warp; arithmetic identical
+// to swiglu_quant_kernel (decode_ops.cu), so the records carry the same bits as the separate operator. ----
+__device__ __forceinline__ void swiglu_tile_epilogue(const MatvecParams& p, const float* sy /*[TILE_ROWS]*/, int64_t tile_in_weight, int rec_row, int lane) {
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        const int j = 32 * b + lane, w_ = j >> 2, g_ = j & 3;
+        const float gv = sy[8 * w_ + g_], uv = sy[8 * w_ + 4 + g_];
+        const float v = __fmul_rn(__fdiv_rn(gv, __fadd_rn(1.0f, det_expf(-gv))), uv);
+        const int64_t f = 64 * tile_in_weight + 32 * b;  // first ffn index of this block (F % 64 == 0: blocks are all-valid or absent)
+        if (f < p.epi_F) quant_block_to_record(v, p.xq_out + ((size_t)(f / CHUNK_K) * p.epi_rows + rec_row) * ACT_REC_BYTES, (int)((f % CHUNK_K) / 32), lane);
+    }
+}
+
+template <class F, int MB, bool PRO, bool GRP, int OUT>
 __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
+    constexpr bool RP = OUT == OUT_REMOTE;
+    constexpr bool EPI = OUT == OUT_SWIGLU;
+    __shared__ float s_y[EPI ? 2 : 1][EPI ? MB : 1][EPI ? TILE_ROWS : 1];   // finished full tiles (double-buffered)
+    __shared__ float s_yfix[EPI ? MB : 1][EPI ? TILE_ROWS : 1];             // finished split tile (fix-up warp only)
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + MV_MAX_STAGES;
@@ -175,22 +264,43 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         p.trace[g * 8 + 2] = smid;
     }
-    const int64_t c0 = sk_begin(g, p.C, G), c1 = sk_begin(g + 1, p.C, G);
+    int64_t c0, c1;
+    if (p.plan32) {  // the usual case: no 64-bit division on the prologue's critical path
+        c0 = sk_begin32((uint32_t)g, (uint32_t)p.C, (uint32_t)G);
+        c1 = sk_begin32((uint32_t)g + 1u, (uint32_t)p.C, (uint32_t)G);
+    } else {
+        c0 = sk_begin(g, p.C, G);
+        c1 = sk_begin(g + 1, p.C, G);
+    }
     const int n_chunks = (int)(c1 - c0);
     const int KC = (int)p.KC;
     const int nst = p.nstages;
     SkPlan& sp = *reinterpret_cast<SkPlan*>(smem + 2 * MV_MAX_STAGES * 8);       // shared plan (computed once)
+    pdl_launch_dependents();  // let the next kernel of the stream start its own weight prefetch
 
-    if (tid == 0) {
-        sp = sk_plan(c0, c1, p.KC);
+    // The producer lane initialises the barriers and requests the first ring-full of weights BEFORE the CTA-wide barrier:
+    // the TMA stream starts a few hundred cycles after the CTA lands on the SM, while thread 0 publishes the plan.
+    const bool is_producer = warp == MV_CONSUMER_WARPS && lane == 0;
+    SkPlan spp;  // the producer's private copy of the plan
+    if (is_producer) {
+        spp = p.plan32 ? sk_plan32((uint32_t)c0, (uint32_t)c1, (uint32_t)p.KC) : sk_plan(c0, c1, p.KC);
         for (int s = 0; s < nst; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], MV_CONSUMER_WARPS);
         }
         fence_mbar_init();
         fence_proxy_async();
+        if (!GRP) {
+            const uint64_t pol0 = policy_evict_first();
+            const uint32_t xbytes0 = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
+            const int pre0 = n_chunks < nst ? n_chunks : nst;
+            for (int j = 0; j < pre0; j++) {
+                mbar_arrive_expect_tx(&full[j], (uint32_t)p.chunk_bytes + xbytes0);
+                bulk_g2s_hint(stages + (size_t)j * p.stage_bytes, p.w + sk_chunk_at(spp, c0, j) * (int64_t)p.chunk_bytes, (uint32_t)p.chunk_bytes, &full[j], pol0);
+            }
+        }
     }
-    pdl_launch_dependents();  // let the next kernel of the stream start its own weight prefetch
+    if (tid == 0) sp = p.plan32 ? sk_plan32((uint32_t)c0, (uint32_t)c1, (uint32_t)p.KC) : sk_plan(c0, c1, p.KC);
     __syncthreads();
 
     if (warp == MV_CONSUMER_WARPS) {
@@ -242,7 +352,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 }
                 bulk_g2s_hint(st, src, wbytes, bar, pol);
             };
-            for (int j = 0; j < pre; j++) issue_w(j, stages + (size_t)j * p.stage_bytes, &full[j]);
+            if (GRP)  // (the plain forms requested their first ring-full ahead of the CTA barrier)
+                for (int j = 0; j < pre; j++) issue_w(j, stages + (size_t)j * p.stage_bytes, &full[j]);
             int npf = n_chunks - pre;
             if (npf > p.l2_prefetch_chunks) npf = p.l2_prefetch_chunks;
             for (int j = pre; j < pre + npf; j++)
@@ -281,79 +392,120 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         // Runs beside the consumers (they only bar.arrive), so neither the math nor the TMA stream ever waits
         // for an atomic round trip.  Split tiles are processed first, so this finishes long before the CTA does.
         constexpr bool rp_on = RP;
-        if (sp.nH == 0 && sp.nT == 0) {
+        if (sp.nH == 0 && sp.nT == 0 && !EPI) {
             if (rp_on) named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
             return;
         }
         pdl_wait();
         RpState rp{0u, 0};
         if constexpr (RP) rp = rp_begin(p);
-        // arrival bookkeeping is computed before the barriers: only the atomic round trip is on the critical path
+        // Split tiles: every contributor leaves its 128 x MB partial sums in its own workspace slot and moves on; ONE designated
+        // contributor per tile -- a CTA whose share of the tile is the last thing it computes -- polls the slots until every
+        // value has landed, sums them in CTA order (deterministic) and writes y.  The slots double as their own ready flags:
+        // the workspace is zero-filled, contributors store -0.0 for an exact zero, so +0.0 bits mean "not written yet", and
+        // the reducer restores +0.0 after reading.  One L2 visibility latency after the last partial store, instead of a
+        // release fence + atomic round trip + load round trip behind it (measured 2-3.8 us of tail per launch in round 2).
         int64_t tqs[2] = {sp.tH, sp.tT};
-        int gfs[2], ncs[2], sgfs[2];
-#pragma unroll
-        for (int seg = 0; seg < 2; seg++) {
-            const int64_t gf = sk_owner(tqs[seg] * p.KC, p.C, G), gl = sk_owner((tqs[seg] + 1) * p.KC - 1, p.C, G);
-            gfs[seg] = (int)gf;
-            ncs[seg] = (int)(gl - gf + 1);
-            sgfs[seg] = (sk_begin(gf, p.C, G) == tqs[seg] * p.KC) ? 0 : 1;  // later contributors start inside the tile: slot 0
-        }
 #pragma unroll
         for (int seg = 0; seg < 2; seg++) {
             if ((seg == 0 ? sp.nH : sp.nT) == 0) continue;
             const int64_t tq = tqs[seg];
-            const int gf = gfs[seg], gl = gfs[seg] + ncs[seg] - 1, nc = ncs[seg], sgf = sgfs[seg];
-            named_bar_sync(2 + seg, MV_CONSUMER_WARPS * 32 + 32);  // every consumer warp stored its share of this tile
+            int gf, gl;
+            if (p.plan32) {
+                gf = (int)((((uint32_t)(tq * p.KC) + 1u) * (uint32_t)G - 1u) / (uint32_t)p.C);
+                gl = (int)((((uint32_t)((tq + 1) * p.KC - 1) + 1u) * (uint32_t)G - 1u) / (uint32_t)p.C);
+            } else {
+                gf = (int)sk_owner(tq * p.KC, p.C, G);
+                gl = (int)sk_owner((tq + 1) * p.KC - 1, p.C, G);
+            }
+            const int nc = gl - gf + 1;
+            const int reducer = nc >= 3 ? gf + 1 : gf;   // a middle contributor finishes at the very end of its life; else the first one
+            if ((int)g != reducer) continue;
+            const int sgf = ((p.plan32 ? (int64_t)sk_begin32((uint32_t)gf, (uint32_t)p.C, (uint32_t)G) : sk_begin(gf, p.C, G)) == tq * p.KC) ? 0 : 1;
             if (p.trace && lane == 0) p.trace[g * 8 + 5] = globaltimer_ns();
-            unsigned int old = 0;
-            if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.ws_cnt + tq) : "memory");
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (p.trace && lane == 0) p.trace[g * 8 + 6] = globaltimer_ns();
-            if (old != (unsigned int)(nc - 1)) continue;  // a later arriver reduces this tile
-            // last arriver: sum the partials in CTA order (deterministic).  Every load of a batch of NB contributors
-            // x all passes is issued before the first add, so the reduction costs one L2 round trip per NB contributors.
             const int64_t tql = GRP ? tq % p.tpw : tq;                      // tile index inside its weight
             const int64_t ybase = GRP ? (tq / p.tpw) * p.y_slot_stride : 0;  // grouped: output of slot tq / tpw
             constexpr int PASSES = 2 * MB;                       // 64 doubles (one double2 per lane) per pass
-            constexpr int NB = MB == 1 ? 8 : (MB == 2 ? 4 : 2);  // contributors in flight
             double2 sum[PASSES];
 #pragma unroll
             for (int v = 0; v < PASSES; v++) sum[v] = make_double2(0.0, 0.0);
+            constexpr int NB = MB == 1 ? 4 : (MB == 2 ? 2 : 1);  // contributors polled together (one L2 round trip per batch when ready); 32 registers
             for (int g0 = gf; g0 <= gl; g0 += NB) {
                 double2 tb[NB][PASSES];
+                for (int spin = 0; spin < (1 << 22); spin++) {  // bounded: a lost contributor must not hang the GPU
+                    bool ready = true;
+#pragma unroll
+                    for (int u = 0; u < NB; u++) {
+                        const int gg = g0 + u;
+                        const double* src = p.ws_part + ((size_t)gg * 2 + (gg == gf ? sgf : 0)) * (TILE_ROWS * MB) + lane * 2;
+#pragma unroll
+                        for (int v = 0; v < PASSES; v++) {
+                            if (gg <= gl) {
+                                asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(tb[u][v].x), "=d"(tb[u][v].y) : "l"(src + v * 64));
+                            } else {
+                                tb[u][v] = make_double2(-0.0, -0.0);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < NB; u++)
+#pragma unroll
+                        for (int v = 0; v < PASSES; v++) ready = ready && __double_as_longlong(tb[u][v].x) != 0ll && __double_as_longlong(tb[u][v].y) != 0ll;
+                    if (__all_sync(0xffffffffu, ready)) break;
+                }
 #pragma unroll
                 for (int u = 0; u < NB; u++) {
                     const int gg = g0 + u;
-                    const double* src = p.ws_part + ((size_t)gg * 2 + (gg == gf ? sgf : 0)) * (TILE_ROWS * MB) + lane * 2;
+                    double* src = p.ws_part + ((size_t)gg * 2 + (gg == gf ? sgf : 0)) * (TILE_ROWS * MB) + lane * 2;
 #pragma unroll
-                    for (int v = 0; v < PASSES; v++)
-                        tb[u][v] = (gg <= gl) ? __ldcg(reinterpret_cast<const double2*>(src + v * 64)) : make_double2(0.0, 0.0);
+                    for (int v = 0; v < PASSES; v++) {
+                        sum[v].x += tb[u][v].x;
+                        sum[v].y += tb[u][v].y;
+                        if (gg <= gl) *reinterpret_cast<double2*>(src + v * 64) = make_double2(0.0, 0.0);   // slot free for the next launch
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < NB; u++)
-#pragma unroll
-                    for (int v = 0; v < PASSES; v++) { sum[v].x += tb[u][v].x; sum[v].y += tb[u][v].y; }
             }
 #pragma unroll
             for (int v = 0; v < PASSES; v++) {
                 const int idx = (v * 32 + lane) * 2;
-                const double sv[2] = {sum[v].x, sum[v].y};
+                // an exact zero was published as -0.0; the sum of zeros is +0.0 (as the oracle's accumulation from +0.0)
+                const double sv[2] = {sum[v].x == 0.0 ? 0.0 : sum[v].x, sum[v].y == 0.0 ? 0.0 : sum[v].y};
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int rr = (idx + e) / MB, m = (idx + e) % MB;
                     const int64_t n = tql * TILE_ROWS + rr;
-                    if (n < p.N && m < p.M) mv_store<RP>(p, rp, ybase + (int64_t)m * p.ldy + n, sv[e] + (mv_use_bias<RP>(p) ? (double)p.bias[n] : 0.0));
+                    if constexpr (EPI) {
+                        if (m < p.M) s_yfix[m][rr] = (float)(sv[e] + ((p.bias && n < p.N) ? (double)p.bias[n] : 0.0));
+                    } else {
+                        if (n < p.N && m < p.M) mv_store<RP>(p, rp, ybase + (int64_t)m * p.ldy + n, sv[e] + (mv_use_bias<RP>(p) ? (double)p.bias[n] : 0.0));
+                    }
                 }
             }
-            if (lane == 0) p.ws_cnt[tq] = 0u;
+            if constexpr (EPI) {
+                __syncwarp();
+                for (int m = 0; m < p.M; m++) swiglu_tile_epilogue(p, s_yfix[m], tql, GRP ? (int)(tq / p.tpw) : m, lane);
+                __syncwarp();
+            }
             if (p.trace && lane == 0) p.trace[g * 8 + 7] = globaltimer_ns();
+        }
+        if constexpr (EPI) {
+            // full tiles of this CTA, in the consumers' order: wait for the tile, activate + quantise it, hand the buffer back
+            const int n_full = sp.nF / KC;
+            for (int ft = 0; ft < n_full; ft++) {
+                const int buf = ft & 1;
+                const int64_t tq = (int64_t)sp.tF + ft;
+                named_bar_sync(MV_BAR_EPI_FULL + buf, MV_CONSUMER_WARPS * 32 + 32);
+                for (int m = 0; m < p.M; m++) swiglu_tile_epilogue(p, s_y[buf][m], GRP ? tq % p.tpw : tq, GRP ? (int)(tq / p.tpw) : m, lane);
+                __syncwarp();
+                asm volatile("bar.arrive %0, %1;" ::"r"(MV_BAR_EPI_FREE + buf), "r"(MV_CONSUMER_WARPS * 32 + 32) : "memory");
+            }
         }
         if (rp_on) named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
         return;
     }
 
     // ===================== consumers =====================
-    pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
+    if constexpr (!PRO) pdl_wait();  // y, the workspace and the bias may still be in use by the preceding kernel before this point
     RpState rp{0u, 0};
     if constexpr (RP) rp = rp_begin(p);
     const int g4 = lane >> 3, i = lane & 7;
@@ -367,7 +519,22 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
 #pragma unroll
         for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
 
-    if (PRO) fused_prologue<MB>(p, xhat, tid, warp, lane, g == 0);
+    if constexpr (PRO) {
+        if (p.pro == 1) {
+            // norm prologue: K = EPT * 512 with EPT in {1, 2, 4, 8, 16} (checked by the host)
+            __shared__ double s_red[MV_CONSUMER_WARPS];
+            switch ((int)p.KC * CHUNK_K / (MV_CONSUMER_WARPS * 32)) {
+                case 16: { float nw[16]; load_nw<16>(p.norm_w, tid, nw); pdl_wait_again(); norm_prologue<MB, 16>(p, xhat, nw, tid, warp, lane, g == 0, s_red); break; }
+                case 8: { float nw[8]; load_nw<8>(p.norm_w, tid, nw); pdl_wait_again(); norm_prologue<MB, 8>(p, xhat, nw, tid, warp, lane, g == 0, s_red); break; }
+                case 4: { float nw[4]; load_nw<4>(p.norm_w, tid, nw); pdl_wait_again(); norm_prologue<MB, 4>(p, xhat, nw, tid, warp, lane, g == 0, s_red); break; }
+                case 2: { float nw[2]; load_nw<2>(p.norm_w, tid, nw); pdl_wait_again(); norm_prologue<MB, 2>(p, xhat, nw, tid, warp, lane, g == 0, s_red); break; }
+                default: { float nw[1]; load_nw<1>(p.norm_w, tid, nw); pdl_wait_again(); norm_prologue<MB, 1>(p, xhat, nw, tid, warp, lane, g == 0, s_red); break; }
+            }
+        } else {
+            pdl_wait_again();
+            fused_prologue<MB>(p, xhat, tid, warp, lane, g == 0);
+        }
+    }
 
     // segment walk: 0 = head (partial, slot 0), 1 = tail (partial, slot 1), 2 = full tiles
     int kcur = sp.nH > 0 ? sp.kcH : 0;  // k-chunk index of the chunk being processed (fused prologue addressing)
@@ -376,6 +543,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     int t = seg == 0 ? sp.tH : (seg == 1 ? sp.tT : sp.tF);
     int s = 0;
     uint32_t ph = 0;
+    int n_full_done = 0;  // OUT_SWIGLU: full tiles flushed so far (selects the s_y buffer)
     for (int j = 0; j < n_chunks; j++) {
         mbar_wait(&full[s], ph);
         if (p.trace && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
@@ -448,7 +616,26 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 acc[s4][m] = v;
             }
-        if (seg == 2) {
+        if (EPI && seg == 2) {
+            // finished full tile -> shared memory (f32, as the unfused path stores it) -> the fix-up warp's SwiGLU epilogue
+            const int buf = n_full_done & 1;
+            if (n_full_done >= 2) named_bar_sync(MV_BAR_EPI_FREE + buf, MV_CONSUMER_WARPS * 32 + 32);  // tile n-2 has been consumed
+            if (i == 0) {
+                const int64_t tl = GRP ? t % p.tpw : t;
+#pragma unroll
+                for (int s4 = 0; s4 < MV_STEPS; s4++) {
+                    const int rr = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
+                    const int64_t n = tl * TILE_ROWS + rr;
+                    const double bv = (p.bias && n < p.N) ? (double)p.bias[n] : 0.0;
+#pragma unroll
+                    for (int m = 0; m < MB; m++) s_y[buf][m][rr] = (float)(acc[s4][m] + bv);
+                }
+                __threadfence_block();
+            }
+            __syncwarp();
+            asm volatile("bar.arrive %0, %1;" ::"r"(MV_BAR_EPI_FULL + buf), "r"(MV_CONSUMER_WARPS * 32 + 32) : "memory");
+            n_full_done++;
+        } else if (seg == 2) {
             if (i == 0) {
 #pragma unroll
                 const int64_t tl = GRP ? t % p.tpw : t;
@@ -471,12 +658,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int s4 = 0; s4 < MV_STEPS; s4++) {
                     const int rr = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
 #pragma unroll
-                    for (int m = 0; m < MB; m++) part[rr * MB + m] = acc[s4][m];
+                    for (int m = 0; m < MB; m++) {
+                        const double v = acc[s4][m];
+                        // +0.0 bits mean "slot not written yet" to the tile's reducer: publish an exact zero as -0.0
+                        asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(part + rr * MB + m), "d"(v == 0.0 ? -0.0 : v) : "memory");
+                    }
                 }
-                __threadfence_block();
             }
-            __syncwarp();
-            asm volatile("bar.arrive %0, %1;" ::"r"(2 + seg), "r"(MV_CONSUMER_WARPS * 32 + 32) : "memory");
         }
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++)
@@ -512,13 +700,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }
 
-template <class F, int MB, bool PRO, bool GRP, bool RP = false>
+template <class F, int MB, bool PRO, bool GRP, int OUT = OUT_PLAIN>
 static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStream_t st) {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + static shared memory (epilogue tiles, reductions) <= 227 KB
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -532,7 +720,7 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP, RP>, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP, OUT>, p);
     if (le != cudaSuccess) return le;
     count_launch();
     return cudaGetLastError();
@@ -540,13 +728,24 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
 
 template <class F>
 static cudaError_t launch_f(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
-    if (p.w_table) return mb == 1 && !p.pro && !p.rp_mode ? launch_t<F, 1, false, true>(p, grid, smem, st) : cudaErrorInvalidValue;
+    if (p.w_table) {
+        if (mb != 1 || p.pro || p.rp_mode) return cudaErrorInvalidValue;
+        return p.xq_out ? launch_t<F, 1, false, true, OUT_SWIGLU>(p, grid, smem, st) : launch_t<F, 1, false, true>(p, grid, smem, st);
+    }
     if (p.rp_mode != RP_NONE) {  // fused tensor-parallel exchange (row-parallel o / down, vocabulary-parallel lm_head)
-        if (p.pro) return cudaErrorInvalidValue;
+        if (p.pro || p.xq_out) return cudaErrorInvalidValue;
         switch (mb) {
-            case 1: return launch_t<F, 1, false, false, true>(p, grid, smem, st);
-            case 2: return launch_t<F, 2, false, false, true>(p, grid, smem, st);
-            case 4: return launch_t<F, 4, false, false, true>(p, grid, smem, st);
+            case 1: return launch_t<F, 1, false, false, OUT_REMOTE>(p, grid, smem, st);
+            case 2: return launch_t<F, 2, false, false, OUT_REMOTE>(p, grid, smem, st);
+            case 4: return launch_t<F, 4, false, false, OUT_REMOTE>(p, grid, smem, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    if (p.xq_out) {  // fused SwiGLU + quantise epilogue (interleaved gate|up weight)
+        switch (mb) {
+            case 1: return p.pro ? launch_t<F, 1, true, false, OUT_SWIGLU>(p, grid, smem, st) : launch_t<F, 1, false, false, OUT_SWIGLU>(p, grid, smem, st);
+            case 2: return p.pro ? launch_t<F, 2, true, false, OUT_SWIGLU>(p, grid, smem, st) : launch_t<F, 2, false, false, OUT_SWIGLU>(p, grid, smem, st);
+            case 4: return p.pro ? launch_t<F, 4, true, false, OUT_SWIGLU>(p, grid, smem, st) : launch_t<F, 4, false, false, OUT_SWIGLU>(p, grid, smem, st);
             default: return cudaErrorInvalidValue;
         }
     }

@@ -43,6 +43,26 @@ __device__ __forceinline__ SkPlan sk_plan(int64_t c0, int64_t c1, int64_t KC) {
     return s;
 }
 
+// 32-bit forms (the host guarantees (C + 1) * G < 2^32): a 64-bit division is a ~150-instruction subroutine on the GPU and
+// the plan sits on the critical path of every launch's prologue
+__device__ __forceinline__ uint32_t sk_begin32(uint32_t g, uint32_t C, uint32_t G) { return g * C / G; }
+__device__ __forceinline__ SkPlan sk_plan32(uint32_t c0, uint32_t c1, uint32_t KC) {
+    SkPlan s;
+    const uint32_t t0 = c0 / KC, t1 = (c1 - 1) / KC;
+    const uint32_t kc0 = c0 - t0 * KC;
+    const uint32_t head_end = (kc0 != 0 || c1 < (t0 + 1) * KC) ? ((t0 + 1) * KC < c1 ? (t0 + 1) * KC : c1) : c0;
+    s.nH = (int)(head_end - c0);
+    s.kcH = (int)kc0;
+    s.tH = (int)t0;
+    uint32_t tail_begin = c1;
+    if (c1 > head_end && c1 != (t1 + 1) * KC) tail_begin = t1 * KC > head_end ? t1 * KC : head_end;
+    s.nT = (int)(c1 - tail_begin);
+    s.tT = (int)t1;
+    s.nF = (int)(tail_begin - head_end);
+    s.tF = (int)(head_end / KC);
+    return s;
+}
+
 // index (in the tile-major chunk array) of the j-th chunk a CTA with range [c0, ...) and plan sp processes
 __device__ __forceinline__ int64_t sk_chunk_at(const SkPlan& sp, int64_t c0, int j) {
     if (j < sp.nH) return c0 + j;

@@ -191,6 +191,13 @@ class Decoder:
         self.weight_bytes = 0
         self.layers = []
         M = batch
+        import os as _os
+        # fused SwiGLU epilogue (b200q_matmul_q8_swiglu): gate|up rows interleaved per tile at upload, the gate|up matvec writes the
+        # down projection's activation records itself -- one launch and one kernel boundary less per layer.  ggml formats only
+        # (the INT4 layouts pack 8 output rows per word), gate and up of one format, F % 64 == 0.
+        dstep = _os.environ.get("B200Q_DSTEP", "0") != "0"   # experimental op-list kernel: keeps the separate operators
+        self.swiglu_epi_wanted = ((not self.wide) and _os.environ.get("B200Q_SWIGLU_EPI", "1") != "0" and self.ff % 64 == 0 and not dstep
+                                  and _os.environ.get("B200Q_FUSED_SWIGLU", "0") == "0")
         for i in range(cfg.n_layers):
             # formats come from the weights themselves when a host model (tests, GGUF files) is given
             fm = {p_: host.layers[i][p_].fmt for p_ in ("q", "k", "v", "o", "gate", "up", "down")} if host else layer_formats(cfg, scheme, i)
@@ -201,7 +208,9 @@ class Decoder:
                                          ("v", fm["v"], cfg.n_kv_heads * hd, pl.kv_rows[0], self.kvd)], H, host)
             # row-parallel o: K slice = this rank's heads
             lay["o"] = self._fused(i, [("o", fm["o"], H, 0, H)], cfg.n_heads * hd, host, kslice=pl.o_cols)
-            lay["gu"] = self._fused(i, [("gate", fm["gate"], cfg.ffn, f0, self.ff), ("up", fm["up"], cfg.ffn, f0, self.ff)], H, host)
+            lay["swiglu_epi"] = self.swiglu_epi_wanted and fm["gate"] == fm["up"] and fm["gate"] in synth.GGML
+            lay["gu"] = self._fused(i, [("gate", fm["gate"], cfg.ffn, f0, self.ff), ("up", fm["up"], cfg.ffn, f0, self.ff)], H, host,
+                                    interleave=lay["swiglu_epi"])
             lay["down"] = self._fused(i, [("down", fm["down"], H, 0, H)], cfg.ffn, host, kslice=(f0, f1))
             an = host.layers[i]["attn_norm"] if host else np.ones(H, np.float32)
             mn = host.layers[i]["mlp_norm"] if host else np.ones(H, np.float32)
@@ -242,7 +251,6 @@ class Decoder:
         else:
             act = lambda K: torch.zeros(int(ops.lib().b200q_act_bytes(C.c_int64(K), C.c_int64(M))), dtype=torch.uint8, device=dev)
             self.xq_h, self.xq_attn, self.xq_ff = act(H), act(self.qd), act(self.ff)
-        import os as _os
         # streaming-order hints: every decode matvec prefetches the head of the next projection's weights into L2 while its own
         # tail drains (qkv -> o -> gate|up -> down -> next layer ... -> lm_head -> layer 0 of the next token)
         if not self.wide and _os.environ.get("B200Q_CHAIN", "0") != "0":  # measured neutral on whole steps (round 2): opt-in
@@ -250,7 +258,11 @@ class Decoder:
             for a, b in zip(order, order[1:] + order[:1]):
                 if a is not b:
                     a.set_next(b)
-        self.fused = _os.environ.get("B200Q_FUSED", "0") != "0" and not self.wide   # add+norm+quant fused into the matvec prologue
+        # add+norm+quant fused into the prologue of the matvec that consumes it (b200q_matmul_norm): measured +3..6 % tok/s on one
+        # GPU.  Needs hidden = 512 * 2^j <= 8192; tensor parallel keeps the separate kernel (it is the exchange's consumer).
+        ept = H // 512
+        self.fused = (_os.environ.get("B200Q_FUSED", "1") != "0" and not self.wide and tp_world == 1 and H % 512 == 0 and ept <= 16
+                      and (ept & (ept - 1)) == 0 and not dstep)
         self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0" and not self.wide  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
@@ -272,8 +284,9 @@ class Decoder:
             self.comm = ops.PeerComm(tp_rank, tp_world, M * H, dev, group, gather_elems=M * self.vs)
 
     # ---- weights ------------------------------------------------------------------------------------
-    def _fused(self, layer: int, parts, K: int, host: Optional[HostModel], kslice=None) -> List[_Linear]:
-        """parts: (name, fmt, N_full, row0, nrows).  Consecutive parts of equal format share one handle."""
+    def _fused(self, layer: int, parts, K: int, host: Optional[HostModel], kslice=None, interleave: bool = False) -> List[_Linear]:
+        """parts: (name, fmt, N_full, row0, nrows).  Consecutive parts of equal format share one handle.
+        interleave: the two parts are gate and up of one format -> rows in the SwiGLU-epilogue order (ops.gate_up_row_order)."""
         out: List[_Linear] = []
         col = 0
         groups = []
@@ -285,13 +298,13 @@ class Decoder:
         for grp in groups:
             fmt = grp[0][1]
             nrows = sum(p[4] for p in grp)
-            w = self._upload(layer, grp, fmt, K, host, kslice)
+            w = self._upload(layer, grp, fmt, K, host, kslice, interleave=interleave)
             self.weight_bytes += w.canonical_bytes
             out.append(_Linear(w, col, w.workspace(self.M)))
             col += nrows
         return out
 
-    def _upload(self, layer: int, grp, fmt: str, K: int, host: Optional[HostModel], kslice) -> ops.QuantWeight:
+    def _upload(self, layer: int, grp, fmt: str, K: int, host: Optional[HostModel], kslice, interleave: bool = False) -> ops.QuantWeight:
         k0, k1 = kslice if kslice is not None else (0, K)
         nrows = sum(p[4] for p in grp)
         if fmt in synth.GGML:
@@ -301,8 +314,12 @@ class Decoder:
                 for (name, _, _, r0, nr) in grp:
                     hl = host.lm_head if layer < 0 else host.layers[layer][name]
                     rows.append(hl.data[r0:r0 + nr])
-                blocks = np.ascontiguousarray(np.concatenate(rows, axis=0))
-            else:
+                blocks = np.concatenate(rows, axis=0)
+                if interleave:
+                    assert len(grp) == 2 and grp[0][4] == grp[1][4]
+                    blocks = blocks[ops.gate_up_row_order(grp[0][4])]
+                blocks = np.ascontiguousarray(blocks)
+            else:  # random blocks generated on the device: any row order is as random as any other
                 seed = 0x5EED + 7919 * (layer + 2) + 131 * _NAME_ID[grp[0][0]] + self.rank
                 if kslice is not None:
                     return self.c.weight_from_ggml(t, random_ggml_device(fmt, nrows, k1 - k0, seed, self.dev), nrows, k1 - k0)
@@ -515,6 +532,21 @@ class Decoder:
                                            None if self.wide else P(self.xq_attn), P(self.xq_attn) if self.wide else None, st))
             in_flight = self._rowpar(lay["o"], self.xq_attn, self.delta)
             delta = self.delta
+            if lay["swiglu_epi"]:
+                # gate|up with the fused SwiGLU epilogue: the matvec writes the down projection's records (xq_ff) itself
+                ln = lay["gu"][0]
+                if fused:
+                    ops._check(L.b200q_matmul_norm_swiglu(ln.w.handle, P(hin), P(delta) if delta is not None else None, P(hout), P(lay["mlp_norm"]),
+                                                          C.c_float(cfg.eps), C.c_int64(M), P(self.xq_ff), C.c_void_p(ln.ws.data_ptr()),
+                                                          C.c_size_t(ln.ws.numel()), st))
+                    hin, hout = hout, hin
+                else:
+                    norm(lay["mlp_norm"])
+                    ops._check(L.b200q_matmul_q8_swiglu(ln.w.handle, P(self.xq_h), C.c_int64(M), P(self.xq_ff), C.c_void_p(ln.ws.data_ptr()),
+                                                        C.c_size_t(ln.ws.numel()), st))
+                in_flight = self._rowpar(lay["down"], self.xq_ff, self.delta2)
+                delta = self.delta2
+                continue
             if fused:
                 matvec_norm(lay["gu"], lay["mlp_norm"], self.gu)
             else:

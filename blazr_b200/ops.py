@@ -55,7 +55,7 @@ EXPORTS = [
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
     "b200q_argmax", "b200q_decode_error", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
-    "b200q_swiglu_f32", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq", "b200q_program_add_attn", "b200q_program_add_argmax", "b200q_program_add_embed",
+    "b200q_swiglu_f32", "b200q_gate_up_row", "b200q_matmul_q8_swiglu", "b200q_matmul_norm_swiglu", "b200q_moe_matmul_q8_swiglu", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq", "b200q_program_add_attn", "b200q_program_add_argmax", "b200q_program_add_embed",
     "b200q_program_finalize", "b200q_program_launch", "b200q_program_free", "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free", "b200q_comm_gather_ptr",
     "b200q_matmul_q8_rowpar", "b200q_allreduce_add_rmsnorm_quant", "b200q_allreduce_finish", "b200q_matmul_q8_gather", "b200q_argmax_gathered", "b200q_allreduce",
     "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         L.b200q_bank_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
         L.b200q_bank_get.restype = C.c_void_p
         L.b200q_weight_set_next.argtypes = [C.c_void_p, C.c_void_p]
+        L.b200q_gate_up_row.restype = C.c_int64
+        L.b200q_gate_up_row.argtypes = [C.c_int64, C.c_int64]
         _lib = L
     return _lib
 
@@ -535,6 +537,13 @@ class PeerComm:
         if self._h is not None:
             lib().b200q_comm_free(self._h)
             self._h = None
+
+
+def gate_up_row_order(F: int) -> np.ndarray:
+    """row permutation of the SwiGLU-epilogue layout (include/b200q.h b200q_gate_up_row): interleaved[r] = concat(gate, up)[perm[r]]"""
+    r = np.arange(2 * F, dtype=np.int64)
+    t, rr = r // 128, r % 128
+    return np.where((rr % 8) // 4 == 1, F, 0) + 64 * t + 4 * (rr // 8) + rr % 4
 
 
 def launch_count() -> int:

@@ -226,6 +226,20 @@ int32_t b200q_matmul_norm(const b200q_weight* w, const float* h_in, const float*
                           void* y, int32_t y_dtype, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
 int32_t b200q_matmul_swiglu(const b200q_weight* w, const float* gate_up, int64_t M, void* y, int32_t y_dtype, int64_t ldy, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* Fused SwiGLU epilogue (M <= 4): `w` is the gate|up projection uploaded with its 2 F rows INTERLEAVED per 128-row tile --
+ * row r of the uploaded matrix is row b200q_gate_up_row(F, r) of the concatenated [gate (F rows); up (F rows)] matrix, i.e.
+ * tile t holds gate/up rows 64 t .. 64 t + 63 with the pair (gate j, up j) in one thread's accumulators (F % 64 == 0).
+ * Every finished tile is activated (silu(gate) * up) and quantised straight into the activation records of the following
+ * down projection (xq_out, b200q_act_bytes(F, M) layout, zero-filled once by the caller): neither the gate|up output nor a
+ * separate SwiGLU launch exists.  Same bits as b200q_matmul_q8 + b200q_swiglu_quant on the un-interleaved weight.
+ * b200q_matmul_norm_swiglu additionally fuses the add + RMSNorm + quantise producer (see b200q_matmul_norm);
+ * b200q_moe_matmul_q8_swiglu is the grouped (expert-bank) form: slot s writes record row s of xq_out (n_slots rows). */
+int64_t b200q_gate_up_row(int64_t F, int64_t r);
+int32_t b200q_matmul_q8_swiglu(const b200q_weight* w, const void* xq, int64_t M, void* xq_out, void* workspace, size_t workspace_bytes, void* stream);
+int32_t b200q_matmul_norm_swiglu(const b200q_weight* w, const float* h_in, const float* delta, float* h_out, const float* norm_w, float eps, int64_t M,
+                                 void* xq_out, void* workspace, size_t workspace_bytes, void* stream);
+int32_t b200q_moe_matmul_q8_swiglu(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const void* xq, int64_t x_rows, int64_t x_slot_div,
+                                   void* xq_out, void* workspace, size_t workspace_bytes, void* stream);
 /* Hint: ask the TMA engine to pull the first `max_bytes` of w (in the order the next b200q_matmul_q8(w, M) will
  * stream them) into L2.  Enqueue it right after the preceding matmul: it overlaps the operators in between. */
 int32_t b200q_weight_prefetch_l2(const b200q_weight* w, int64_t M, int64_t max_bytes, void* stream);
