@@ -5,8 +5,9 @@ A *step* is one decode token of the named random-init model: every quantized pro
 (4 fused matvec launches per layer + lm_head; 7L+1 projections) plus the glue operators, replayed from one
 CUDA graph (the caller pattern of reference src/engine/cuda_graphs.rs:166-189).
 
-    python bench.py --gpus 1 --steps 128 --warmup 16                 # Mistral-7B GGUF Q6_K, batch-1 decode
-    torchrun ... bench.py --gpus N ...                               # same model, tensor-parallel over N GPUs
+    python bench.py --gpus 1 --steps 128 --warmup 16                 # Llama-3-70B GGUF Q4_K_M, batch-1 decode
+    torchrun ... bench.py --gpus N ...                               # same model, tensor-parallel over N GPUs (fused NVLink exchange)
+    python bench.py --workload mistral-7b:Q6_K                       # any other preset:scheme (also reported in extra.configs)
     python bench.py --impl reference ...                             # the CPU path (oracle port) on host cores
 
 JSON line (one, from rank 0): value = tokens/s with inputs resident in HBM (graph replay, device timed);
@@ -35,7 +36,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mistral-7b:Q6_K", help="<model preset>:<scheme>  e.g. llama-3-70b:Q4_K_M, llama-3-8b:AWQ")
+    ap.add_argument("--workload", default="llama-3-70b:Q4_K_M", help="<model preset>:<scheme>  e.g. mistral-7b:Q6_K, llama-3-8b:AWQ (default: the config "
+                    "BASELINE.json's target sentence names; it fits one B200 at 42 GB and runs tensor-parallel at --gpus N)")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--prompt", type=int, default=32, help="prompt tokens fed before the timed region (reference bench.rs:24)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (prefill GEMM, batch-32)")
@@ -252,10 +254,22 @@ def run_b200(args):
     pk, pk_kind = peaks()
     gu = [lay["gu"][0] for lay in dec.layers]
     reps = 20
+    import ctypes as C
+    L_ = ops.lib()
+    P_ = lambda t_: C.c_void_p(t_.data_ptr())
+    epi = bool(dec.layers[0]["swiglu_epi"])
+    gu_variant = ("norm prologue + " if (dec.fused and epi) else "") + ("SwiGLU epilogue" if epi else "plain")
 
-    def run_gu():
-        for ln in gu:
-            dec._matvec([ln], dec.xq_h, dec.gu)
+    def run_gu():  # the same entry point (kernel variant) the decode step launches for gate|up, over every layer's weight
+        st_ = ops._stream_ptr(dev)  # the CURRENT stream (the capturing one inside torch.cuda.graph)
+        for lay, ln in zip(dec.layers, gu):
+            if epi and dec.fused:
+                ops._check(L_.b200q_matmul_norm_swiglu(ln.w.handle, P_(dec.h), None, P_(dec.h2), P_(lay["mlp_norm"]), C.c_float(cfg.eps), C.c_int64(M),
+                                                       P_(dec.xq_ff), P_(ln.ws), C.c_size_t(ln.ws.numel()), st_))
+            elif epi:
+                ops._check(L_.b200q_matmul_q8_swiglu(ln.w.handle, P_(dec.xq_h), C.c_int64(M), P_(dec.xq_ff), P_(ln.ws), C.c_size_t(ln.ws.numel()), st_))
+            else:
+                dec._matvec([ln], dec.xq_h, dec.gu)
 
     run_gu()
     torch.cuda.synchronize(dev)
@@ -283,22 +297,28 @@ def run_b200(args):
     # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/, tools/ncu_summary.py)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         tk = tj.get(f"{decode.layer_formats(cfg, scheme, 0)['gate']}:{w0.N}x{w0.K}:M{M}")
         if tk:
             traffic = tk["dram_bytes_read"] + tk["dram_bytes_write"]
     except Exception:
         traffic = None
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-            "kernel": f"matvec_kernel<{decode.layer_formats(cfg, scheme, 0)['gate']},{M}> gate|up N={w0.N} K={w0.K}", "us_per_launch": us_gu,
+            "kernel": f"matvec_kernel<{decode.layer_formats(cfg, scheme, 0)['gate']}, MB={M}> gate|up N={w0.N} K={w0.K} ({gu_variant})", "us_per_launch": us_gu,
             "algorithmic_bytes_per_launch": bytes_gu, "peak_kind": pk_kind + " burst (kernel timed alone)",
             "step_weight_bytes": step_bytes, "step_GBs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
             "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"]}
 
+    launches_per_step = dec.launches_per_step()
     extra = {}
     if not args.no_extra and rank == 0 and world == 1:
         try:
-            extra = extras(client, cfg, scheme, pk)
+            # the headline model (42 GB for the default) is released first: the extras build their own models
+            del g2, g, gu
+            dec.graph = None
+            del dec
+            torch.cuda.empty_cache()
+            extra = extras(client, cfg, scheme, pk, args)
         except Exception as ex:  # secondary measurements must never take the headline line down
             extra = {"error": repr(ex)[:300]}
 
@@ -311,11 +331,11 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int8 activations x int4/6/8 weights, f64-exact accumulate -> f32", "data": "synthetic",
             "config": {"workload": f"{model} GGUF {scheme} random-init, batch-{M} greedy decode, {args.prompt}-token prompt then {args.steps} tokens",
-                       "parallelism": f"tp{world}", "l2": f"weights {step_bytes * world / 1e9:.1f} GB streamed once per token (>> 126 MB L2)",
-                       "launches_per_step": dec.launches_per_step()},
+                       "parallelism": f"tp{world}" + (" (fused NVLink exchange: row-parallel matvec pushes, norm / arg-max consume)" if world > 1 else ""), "l2": f"weights {step_bytes * world / 1e9:.1f} GB streamed once per token (>> 126 MB L2)",
+                       "launches_per_step": launches_per_step},
             "clocks": clocks,
             "e2e": {"value": toks_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8 * M, "d2h_bytes_per_step": 8 * M},
-            "gpu_launches": dec.launches_per_step() * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
             "impl": "b200",
         }
@@ -334,42 +354,161 @@ def run_b200(args):
         os._exit(0)
 
 
-def extras(client, cfg, scheme, pk):
-    """secondary numbers of the north_star: prefill dequant-GEMM TFLOP/s and batch-32 decode through the
-    tcgen05 path on one projection shape (kernel level)."""
+def time_decode(dec, steps: int, warmup: int = 6, prompt: int = 16):
+    """tokens/s of a captured decode step (graph replay, device timed), after `prompt` context tokens"""
+    import torch
+
+    dec.capture()
+    dec.reset([1] * dec.M)
+    for _ in range(prompt + warmup):
+        dec.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dec.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dec.M / (ms * 1e-3), ms
+
+
+def matvec_shape_table(client, pk):
+    """kernel GB/s of the decode matvec for every projection shape of the 7B/8B configs x the north_star's lead formats:
+    one launch per rotating weight copy (copies > 2x L2), graph replay, CUDA events (tools/kbench.py method)."""
+    import torch
+
+    from blazr_b200 import decode, ops, synth
+
+    shapes = [("qkv", 6144, 4096), ("o", 4096, 4096), ("gate|up", 28672, 4096), ("down", 4096, 14336), ("lm_head", 32000, 4096)]
+    rows = []
+    dev = client.device
+    for fmt in ("Q4_K", "Q6_K", "Q8_0", "AWQ"):
+        for name, N, K in shapes:
+            def mk(i):
+                if fmt in synth.GGML:
+                    return client.weight_from_ggml(synth.GGML[fmt], decode.random_ggml_device(fmt, N, K, 300 + i, dev), N, K)
+                qw, sc, z = decode.random_int4_device(fmt, N, K, 128, 300 + i, dev)
+                return client.weight_from_decomposed(ops.DecomposedQuantTensor(qw, sc, z, None, ops.DecomposedQuantMethod("awq", 128), (N, K)))
+            w0 = mk(0)
+            copies = int(min(48, max(2, -(-300e6 // w0.canonical_bytes))))
+            ws = [w0] + [mk(i) for i in range(1, copies)]
+            xq = client.quantize_act(torch.randn((1, K), device=dev))
+            y = torch.empty((1, N), device=dev)
+            wss = [w.workspace(1) for w in ws]
+
+            def run_all():
+                for w, s_ in zip(ws, wss):
+                    client.matmul_q8(xq, 1, w, out=y, workspace=s_)
+
+            run_all()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(g, stream=st):
+                    run_all()
+                for _ in range(3):
+                    g.replay()
+                st.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                reps = 10
+                for _ in range(reps):
+                    g.replay()
+                e1.record(st)
+                st.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (reps * copies)
+            b = w0.canonical_bytes + K * 1.25 + N * 4
+            rows.append({"fmt": fmt, "proj": name, "N": N, "K": K, "us": round(us, 2), "GBs": round(b / (us * 1e-6) / 1e9, 1),
+                         "frac_hbm": round(b / (us * 1e-6) / 1e9 / pk["hbm_gbs"], 3)})
+            del g
+            for w in ws:
+                w.free()
+    return rows
+
+
+def extras(client, cfg, scheme, pk, args):
+    """secondary numbers of the north_star, all driver-run with the default command: (1) batch-1 decode tok/s of the other named
+    configs, (2) the per-shape matvec table, (3) prefill dequant-GEMM TFLOP/s + prefill pass tokens/s, (4) batch-32 decode,
+    (5) a DeepSeek-V2-Lite-shaped MoE layer."""
+    import time
+
     import torch
 
     from blazr_b200 import decode, ops, synth
 
     out = {}
-    fmt = decode.layer_formats(cfg, scheme, 0)["gate"]
-    if fmt not in synth.GGML:
-        return out
+    t_start = time.perf_counter()
+    budget_s = float(os.environ.get("B200Q_BENCH_EXTRA_S", "170"))   # the default run must end within minutes
+    # (1) the other BASELINE configs, batch-1 greedy decode, whole step from one CUDA graph
+    cfgs = []
+    for wl in ("llama-3.2-1b:Q4_K_M", "mistral-7b:Q6_K", "mistral-7b:Q8_0", "mistral-7b:Q4_K", "llama-3-8b:AWQ", "llama-3-8b:GPTQ", "llama-3-70b:Q4_K_M"):
+        if wl == args.workload or time.perf_counter() - t_start > budget_s:
+            continue
+        m_, s_ = wl.split(":")
+        try:
+            d_ = decode.Decoder(client, decode.PRESETS[m_], s_, batch=1, max_ctx=160)
+            toks, ms = time_decode(d_, 48)
+            cfgs.append({"workload": wl, "tokens_per_s": round(toks, 1), "ms_per_step": round(ms, 4), "launches_per_step": d_.launches_per_step(),
+                         "step_frac_hbm": round(d_.weight_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 3)})
+            del d_
+        except Exception as ex:
+            cfgs.append({"workload": wl, "error": repr(ex)[:200]})
+        torch.cuda.empty_cache()
+    out["configs"] = cfgs
+    # (2) per-shape kernel table
+    if time.perf_counter() - t_start < budget_s:
+        try:
+            out["matvec_shapes"] = matvec_shape_table(client, pk)
+        except Exception as ex:
+            out["matvec_shapes"] = {"error": repr(ex)[:200]}
+    # (3)-(5) on the Mistral-7B shapes (BASELINE config 2) whatever the headline workload is
+    cfg = decode.PRESETS["mistral-7b"]
+    scheme = "Q6_K"
+    # prefill dequant-GEMM (tcgen05/TMEM) on the gate projection shape: Mistral-7B Q6_K / Q8_0 at S = 2048 (config 2),
+    # Llama-3-8B AWQ at S = 4096 (config 3); skinny M = 32 (batched decode) on the same weight
     N, K = cfg.ffn, cfg.hidden
-    t = synth.GGML[fmt]
-    copies = 4
-    ws = [client.weight_from_ggml(t, decode.random_ggml_device(fmt, N, K, 100 + i, client.device), N, K) for i in range(copies)]
-    for name, Mx in (("prefill_2048", 2048), ("decode_batch32", 32)):
-        x = torch.randn((Mx, K), device=client.device)
-        y = torch.empty((Mx, N), device=client.device)
-        wss = [w.workspace(Mx) for w in ws]
-        for w, s in zip(ws, wss):
-            client.quant_matmul(x, w, out=y, workspace=s)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record()
-        for _ in range(reps):
-            for w, s in zip(ws, wss):
-                client.quant_matmul(x, w, out=y, workspace=s)
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / (reps * copies)
-        tf = 2.0 * Mx * N * K / (us * 1e-6) / 1e12
-        out[name] = {"shape": f"{fmt} N={N} K={K} M={Mx}", "us": us, "TFLOPs": tf, "frac_bf16_burst": tf / pk["bf16_tflops"],
-                     "GBs": ws[0].canonical_bytes / (us * 1e-6) / 1e9, "includes": "f16 activation staging kernel + tcgen05 GEMM"}
-    for w in ws:
-        w.free()
+    dev = client.device
+
+    def mk_weight(fmt, i):
+        if fmt in synth.GGML:
+            return client.weight_from_ggml(synth.GGML[fmt], decode.random_ggml_device(fmt, N, K, 100 + i, dev), N, K)
+        qw, sc, z = decode.random_int4_device(fmt, N, K, 128, 100 + i, dev)
+        return client.weight_from_decomposed(ops.DecomposedQuantTensor(qw, sc, z, None, ops.DecomposedQuantMethod("awq", 128), (N, K)))
+
+    for name, fmt, Mx in (("prefill_2048", "Q6_K", 2048), ("prefill_2048_q8_0", "Q8_0", 2048), ("prefill_4096_awq", "AWQ", 4096), ("decode_batch32", "Q6_K", 32)):
+        if time.perf_counter() - t_start > budget_s:
+            break
+        try:
+            copies = 4
+            ws = [mk_weight(fmt, i) for i in range(copies)]
+            x = torch.randn((Mx, K), device=dev)
+            if fmt == "AWQ":
+                x = x.half()   # AWQ / GPTQ activations are f16 in blazr (awq.rs:69-71)
+            y = torch.empty((Mx, N), device=dev, dtype=x.dtype)
+            wss = [w.workspace(Mx) for w in ws]
+            for w, s_ in zip(ws, wss):
+                client.quant_matmul(x, w, out=y, workspace=s_)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                for w, s_ in zip(ws, wss):
+                    client.quant_matmul(x, w, out=y, workspace=s_)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (reps * copies)
+            tf = 2.0 * Mx * N * K / (us * 1e-6) / 1e12
+            out[name] = {"shape": f"{fmt} N={N} K={K} M={Mx}", "us": us, "TFLOPs": tf, "frac_bf16_burst": tf / pk["bf16_tflops"],
+                         "frac_bf16_sustained": tf / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                         "GBs": ws[0].canonical_bytes / (us * 1e-6) / 1e9, "includes": "f16 activation staging kernel + tcgen05 GEMM"}
+            for w in ws:
+                w.free()
+        except Exception as ex:
+            out[name] = {"error": repr(ex)[:200]}
     # whole-step batched decode (BASELINE metric: "decode tok/s at batch 1 and batch 32"): 32 sequences, every
     # projection on the tcgen05 path, replayed from one CUDA graph
     try:

@@ -153,6 +153,21 @@ def random_ggml_device(fmt: str, N: int, K: int, seed: int, device) -> torch.Ten
     return blk.reshape(N, K // be * bb)
 
 
+def random_int4_device(kind: str, N: int, K: int, gs: int, seed: int, device):
+    """AWQ / GPTQ tensors of blazr's loader layouts generated directly in HBM (bench: no host round trip).
+    AWQ : qweight u32 [K, N/8], scales f32 [K/gs, N] (f16-representable), zeros f32 [K/gs, N] integers 0..15
+    GPTQ: qweight u32 [K/8, N], scales f32 [G, N], qzeros u32 [G, N/8] packed (no act-order)"""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    G = K // gs
+    u32 = lambda *shape: torch.randint(-2 ** 31, 2 ** 31, shape, dtype=torch.int32, device=device, generator=g)
+    scales = ((torch.rand((G, N), device=device, generator=g) + 0.5) / (4.6 * float(np.sqrt(K)))).to(torch.float16).to(torch.float32)
+    if kind == "AWQ":
+        zeros = torch.randint(0, 16, (G, N), device=device, generator=g).to(torch.float32)
+        return u32(K, N // 8), scales, zeros
+    return u32(K // 8, N), scales, u32(G, N // 8)
+
+
 _NAME_ID = dict(q=1, k=2, v=3, o=4, gate=5, up=6, down=7, lm_head=8)
 
 
@@ -325,7 +340,13 @@ class Decoder:
                     return self.c.weight_from_ggml(t, random_ggml_device(fmt, nrows, k1 - k0, seed, self.dev), nrows, k1 - k0)
                 blocks = random_ggml_device(fmt, nrows, K, seed, self.dev)
             return self.c.weight_from_ggml(t, blocks, nrows, K, cols=(k0, k1) if kslice is not None else None)
-        # AWQ / GPTQ (host models only fuse by concatenating along N)
+        # AWQ / GPTQ
+        if host is None:  # bench: random tensors generated on the device, one fused [nrows, k1 - k0] weight
+            seed = 0x5EED + 7919 * (layer + 2) + 131 * _NAME_ID[grp[0][0]] + self.rank
+            qw, sc, z = random_int4_device(fmt, nrows, k1 - k0, 128, seed, self.dev)
+            dq = ops.DecomposedQuantTensor(qw, sc, z, None, ops.DecomposedQuantMethod(fmt.lower(), 128), (nrows, k1 - k0))
+            return self.c.weight_from_decomposed(dq)
+        # host models: fuse by concatenating along N
         if host is None:
             host_parts = [_host_linear(fmt, p[4], K, 0x5EED + 31 * (layer + 2) + j + 17 * self.rank) for j, p in enumerate(grp)]
             sl = [(hp, 0, hp.N) for hp in host_parts]
