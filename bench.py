@@ -534,36 +534,47 @@ def extras(client, cfg, scheme, pk, args):
     except Exception as ex:  # secondary number: never take the headline down with it
         out["decode_batch32_step"] = {"error": repr(ex)[:200]}
     # MoE decode (BASELINE config 5 shapes: DeepSeek-V2-Lite, 64 routed experts + 2 shared halves, top-6; gate|up Q4_K
-    # [2816 x 2048], down Q8_0 [2048 x 1408] because K = 1408 is not a multiple of 256): one token through the expert MLP =
-    # grouped gate|up matvec over 8 slots, SwiGLU+quantise, grouped down matvec (3 launches), routing rotated every call
+    # [2816 x 2048] in the SwiGLU-epilogue row order, down Q8_0 [2048 x 1408] because K = 1408 is not a multiple of 256): one token
+    # through the expert MLP = quantise, grouped gate|up + SwiGLU epilogue, grouped down, combine -- 4 PDL-chained launches,
+    # 16 different routings captured in ONE CUDA graph (every expert weight is touched, > L2)
     try:
         E, top_k, hidden, ffn = 66, 8, 2048, 1408
         tg, td = synth.GGML["Q4_K"], synth.GGML["Q8_0"]
         gu = [client.weight_from_ggml(tg, decode.random_ggml_device("Q4_K", 2 * ffn, hidden, 500 + e, client.device), 2 * ffn, hidden) for e in range(E)]
         dn = [client.weight_from_ggml(td, decode.random_ggml_device("Q8_0", hidden, ffn, 700 + e, client.device), hidden, ffn) for e in range(E)]
-        moe = ops.MoeMlp(client, [ops.ExpertWeights(g, d) for g, d in zip(gu, dn)], ffn, hidden)
+        moe = ops.MoeMlp(client, [ops.ExpertWeights(g, d, interleaved=True) for g, d in zip(gu, dn)], ffn, hidden)
         x = torch.randn((1, hidden), device=client.device)
         gen = torch.Generator(device="cpu"); gen.manual_seed(3)
         nsel = 16
         sels = [torch.cat([torch.randperm(64, generator=gen)[:6], torch.tensor([64, 65])]).to(torch.int32).reshape(1, top_k).to(client.device) for _ in range(nsel)]
         gw = torch.full((1, top_k), 1.0 / top_k, device=client.device)
-        for sl in sels:
-            moe.forward_decode(x, sl, gw)
+        n0 = ops.launch_count()
+        moe.forward_decode(x, sels[0], gw)
+        per_call = ops.launch_count() - n0
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            for sl in sels:
-                moe.forward_decode(x, sl, gw)
-        e1.record()
-        torch.cuda.synchronize()
+        gm = torch.cuda.CUDAGraph()
+        sm = torch.cuda.Stream()
+        sm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(sm):
+            with torch.cuda.graph(gm, stream=sm):
+                for sl in sels:
+                    moe.forward_decode(x, sl, gw)
+            for _ in range(3):
+                gm.replay()
+            sm.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record(sm)
+            for _ in range(reps):
+                gm.replay()
+            e1.record(sm)
+            sm.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (reps * nsel)
         wbytes = top_k * (gu[0].canonical_bytes + dn[0].canonical_bytes)
         out["moe_decode_layer"] = {"us": us, "GBs": wbytes / (us * 1e-6) / 1e9, "frac_hbm": wbytes / (us * 1e-6) / 1e9 / pk["hbm_gbs"],
-                                   "weight_bytes_per_token": wbytes,
-                                   "what": "DeepSeek-V2-Lite expert MLP, 1 token: 6 routed of 64 + 2 shared halves, Q4_K gate|up + Q8_0 down, eager launches "
-                                           "(quantise, grouped gate|up, SwiGLU, grouped down, torch combine)"}
+                                   "weight_bytes_per_token": wbytes, "launches_per_layer": per_call,
+                                   "what": "DeepSeek-V2-Lite expert MLP, 1 token: 6 routed of 64 + 2 shared halves, Q4_K gate|up + Q8_0 down; quantise, grouped "
+                                           "gate|up with fused SwiGLU epilogue, grouped down, combine; graph replay over 16 routings"}
     except Exception as ex:
         out["moe_decode_layer"] = {"error": repr(ex)[:200]}
     return out

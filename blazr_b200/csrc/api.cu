@@ -266,12 +266,15 @@ int32_t b200q_weight_from_awq(const uint32_t* qweight, const float* scales, cons
     return b200q_weight_from_awq_shard(qweight, scales, zeros, src_on_device, group_size, N, K, 0, N, 0, K, device, stream, out);
 }
 
-int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* g_idx, const float* bias,
-                               int32_t src_on_device, int32_t group_size, int32_t zero_plus_one, int64_t N, int64_t K, int32_t device,
-                               void* stream, b200q_weight** out) {
+int32_t b200q_weight_from_gptq_shard(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* g_idx, const float* bias,
+                                     int32_t src_on_device, int32_t group_size, int32_t zero_plus_one, int64_t N, int64_t K, int64_t n0, int64_t n1,
+                                     int64_t k0, int64_t k1, int32_t device, void* stream, b200q_weight** out) {
     if (!out) return fail(B200Q_ERR_INVALID_ARG, "out is null");
     *out = nullptr;
     if (!qweight || !scales || !qzeros || N <= 0 || K <= 0) return fail(B200Q_ERR_INVALID_ARG, "bad GPTQ arguments");
+    if (n0 < 0 || n1 > N || n0 >= n1 || n0 % 8 || n1 % 8 || k0 < 0 || k1 > K || k0 >= k1 || k0 % group_size || k1 % group_size || k0 % 32)
+        return fail(B200Q_ERR_INVALID_ARG, "bad GPTQ shard range (rows in multiples of 8, K shards group aligned)");
+    const bool k_sharded = k0 != 0 || k1 != K;
     int gpc = gpc_for(group_size);
     if (!gpc) return fail(B200Q_ERR_UNSUPPORTED, "GPTQ group_size %d unsupported (32, 64, 128 or a multiple of 256)", group_size);
     if (N % 8 || K % group_size || K % 8) return fail(B200Q_ERR_INVALID_ARG, "GPTQ needs N %% 8 == 0 and K %% group_size == 0");
@@ -300,13 +303,16 @@ int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, con
             for (int64_t k = 0; k < K; k++) perm[cnt[gi[k]]++] = (int32_t)k;
         }
     }
+    // act-order scatters every group over the whole K axis: a contiguous K slice of the weight does not correspond to a
+    // contiguous slice of the activations (SURVEY.md section 7 "GPTQ act-order g_idx defeats contiguous K-splits")
+    if (need_perm && k_sharded) return fail(B200Q_ERR_UNSUPPORTED, "GPTQ act-order (non-trivial g_idx) weights cannot be split along K");
     b200q_weight* w = new (std::nothrow) b200q_weight();
     if (!w) return fail(B200Q_ERR_CUDA, "out of host memory");
     memset(w, 0, sizeof(*w));
-    w->N = N; w->K = K;
+    w->N = n1 - n0; w->K = k1 - k0;
     w->family = B200Q_FAM_G4; w->source = B200Q_SRC_GPTQ; w->ggml_type = -1; w->group_size = group_size; w->sub = 32; w->gpc = gpc;
     w->chunk_bytes = 128 * 128 + 128 * gpc * 3;
-    w->canonical_bytes = N * K / 2 + N * (K / group_size) * 2 + N * (K / group_size) / 2 + (g_idx ? K * 4 : 0);
+    w->canonical_bytes = w->N * w->K / 2 + w->N * (w->K / group_size) * 2 + w->N * (w->K / group_size) / 2 + (g_idx ? w->K * 4 : 0);
     int32_t rc = alloc_weight(w, device);
     if (rc) { free_weight(w); return rc; }
     std::vector<void*> temps;
@@ -316,8 +322,8 @@ int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, con
         if (e == cudaSuccess) e = cudaMemcpyAsync(w->perm, perm.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st);
     }
     if (e == cudaSuccess && bias) {
-        e = cudaMalloc((void**)&w->bias, (size_t)N * 4);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(w->bias, bias, (size_t)N * 4, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+        e = cudaMalloc((void**)&w->bias, (size_t)w->N * 4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(w->bias, bias + n0, (size_t)w->N * 4, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
     }
     const uint32_t *qd = nullptr, *zd = nullptr; const float* sd = nullptr;
     int64_t G = K / group_size;
@@ -327,8 +333,14 @@ int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, con
     int* err_dev = nullptr;
     if (e == cudaSuccess) { e = cudaMalloc((void**)&err_dev, sizeof(int)); if (e == cudaSuccess) temps.push_back(err_dev); }
     if (e == cudaSuccess) e = cudaMemsetAsync(err_dev, 0, sizeof(int), st);
-    if (e == cudaSuccess) e = launch_repack_gptq(qd, sd, zd, w->perm, zero_plus_one, N, 0, 0, w, err_dev, st);
+    if (e == cudaSuccess) e = launch_repack_gptq(qd, sd, zd, w->perm, zero_plus_one, N, n0, k0, w, err_dev, st);
     return finish_g4(w, err_dev, temps, e, st, out);
+}
+
+int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* g_idx, const float* bias,
+                               int32_t src_on_device, int32_t group_size, int32_t zero_plus_one, int64_t N, int64_t K, int32_t device,
+                               void* stream, b200q_weight** out) {
+    return b200q_weight_from_gptq_shard(qweight, scales, qzeros, g_idx, bias, src_on_device, group_size, zero_plus_one, N, K, 0, N, 0, K, device, stream, out);
 }
 
 int32_t b200q_weight_free(b200q_weight* w) {

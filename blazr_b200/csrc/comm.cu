@@ -41,13 +41,12 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, const T
     __syncthreads();
     if (tid == 0) {
         unsigned int* done = reinterpret_cast<unsigned int*>(mine + COMM_OFF_AR_DONE);
-        __threadfence_system();
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
         unsigned int old;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
         if (old == (unsigned int)(G - 1)) {
             *done = 0u;
-            for (int r = 0; r < c.world; r++)
-                st_release_sys(reinterpret_cast<unsigned int*>(c.peers[r] + COMM_OFF_AR_FLAGS) + par * COMM_MAX_WORLD + c.rank, epoch);
+            comm_raise_flags(c, COMM_OFF_AR_FLAGS, par, epoch);
             *reinterpret_cast<unsigned int*>(mine + COMM_OFF_AR_EPOCH) = epoch;  // every CTA read it before its arrival above
         }
     }

@@ -53,6 +53,13 @@ struct RemoteOut {
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Raise this rank's epoch flag at every rank.  ONE system-scope fence, then `world` fire-and-forget relaxed stores: a
+// st.release.sys per peer would serialise `world` NVLink round trips on the last CTA (measured at TP8: the exchange then costs
+// more than the matvec it follows).  fence + relaxed store is the release pattern of the PTX memory model.
+__device__ __forceinline__ void comm_raise_flags(const struct CommDev& c, int flags_off, int par, unsigned int epoch);
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -63,6 +70,10 @@ __device__ __forceinline__ size_t comm_ar_slot_off(const CommDev& c, int par, in
 }
 __device__ __forceinline__ size_t comm_ag_off(const CommDev& c, int src) {
     return COMM_HDR_BYTES + (size_t)2 * c.world * (size_t)c.slot_elems * sizeof(double) + (size_t)src * (size_t)c.gather_elems * sizeof(float);
+}
+__device__ __forceinline__ void comm_raise_flags(const CommDev& c, int flags_off, int par, unsigned int epoch) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    for (int r = 0; r < c.world; r++) st_relaxed_sys(reinterpret_cast<unsigned int*>(c.peers[r] + flags_off) + par * COMM_MAX_WORLD + c.rank, epoch);
 }
 // consumer side: wait until every rank's flag has reached `epoch` (threads 0..world-1 of the CTA poll; caller syncs)
 __device__ __forceinline__ void comm_wait_flags(const CommDev& c, int flags_off, int par, unsigned int epoch, int tid) {

@@ -181,14 +181,19 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
 // act = silu(gate) * up ; xq = quant(act)       gate_up: [M, 2*F] (gate first), F % 32 == 0; the records are
 // zero-padded up to the next multiple of 256 (DeepSeek-V2-Lite experts: F = 1408 = 5.5 chunks)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restrict__ gu, int F, int M, uint8_t* __restrict__ xq, float* __restrict__ act) {
+// il != 0: gate_up columns are in the SwiGLU-epilogue row order of the weight (b200q_gate_up_row): tile t of 128 columns holds
+// the pairs (gate j, up j), j = 64 t .. 64 t + 63, at columns 128 t + 8 (j%64 / 4) + (j % 4) and + 4.
+__global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restrict__ gu, int F, int M, uint8_t* __restrict__ xq, float* __restrict__ act, int il) {
     pdl_launch_dependents();
     pdl_wait();
     const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
     const int k = kc * CHUNK_K + t;
     float v = 0.0f;
     if (k < F) {
-        const float g = gu[(size_t)m * 2 * F + k], u = gu[(size_t)m * 2 * F + F + k];
+        const int j = k & 63;
+        const size_t cg = il ? (size_t)(k >> 6) * 128 + 8 * (j >> 2) + (j & 3) : (size_t)k;
+        const size_t cu = il ? cg + 4 : (size_t)F + k;
+        const float g = gu[(size_t)m * 2 * F + cg], u = gu[(size_t)m * 2 * F + cu];
         v = __fmul_rn(__fdiv_rn(g, __fadd_rn(1.0f, det_expf(-g))), u);
         if (act) act[(size_t)m * F + k] = v;
     }
@@ -203,10 +208,19 @@ __global__ void __launch_bounds__(256) swiglu_quant_kernel(const float* __restri
 // token; rope: [max_ctx][hd/2][2] (cos, sin).  One CTA of ATT_NT threads per (head, m); dynamic smem = max_ctx f32.
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_NT = 512;  // threads per (head, m): 128 positions per score sweep, so a short context is one round trip
-template <int HD>
+// PAGED (reference src/engine/batch_decode.rs:77-147, forward_with_paged_kv_cache): cache_k / cache_v are block POOLS
+// [num_blocks][block_size][nkv][hd]; position j of sequence m lives in block block_table[m][j / block_size] at offset
+// j % block_size; the new token goes to slot_mapping[m] (= block * block_size + offset; derived from the block table when
+// slot_mapping is null).  max_ctx = max_blocks * block_size bounds the positions.  Same arithmetic, same bits.
+struct PagedKv {
+    const int* block_table;   // [M][max_blocks]
+    const int* slot_mapping;  // [M] or null
+    int block_size, max_blocks;
+};
+template <int HD, bool PAGED>
 __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos, float* __restrict__ cache_k,
                                                            float* __restrict__ cache_v, const float* __restrict__ rope, int nh, int nkv,
-                                                           int max_ctx, int M, uint8_t* __restrict__ xq, float* __restrict__ attn_out) {
+                                                           int max_ctx, int M, uint8_t* __restrict__ xq, float* __restrict__ attn_out, const PagedKv pg) {
     pdl_launch_dependents();
     extern __shared__ float s_sc[];  // scores, then probabilities, for positions 0..p
     const int head = blockIdx.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -215,15 +229,24 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
     // RoPE table, the KV cache or the score buffer: loads ahead of the wait use a clamped position, and after the
     // wait the CTA raises the sticky device error flag (b200q_decode_error) and writes nothing
     const int p_raw = pos[m];
-    const bool bad_pos = p_raw < 0 || p_raw >= max_ctx;
+    bool bad_pos = p_raw < 0 || p_raw >= max_ctx;
+    if constexpr (PAGED) {
+        if (pg.slot_mapping && pg.slot_mapping[m] < 0) bad_pos = true;   // -1 = the block table was too short (batch_decode.rs:88)
+    }
     const int p = bad_pos ? 0 : p_raw;
     const int row = (nh + 2 * nkv) * HD;
     const float* qsrc = qkv + (size_t)m * row + (size_t)head * HD;
     const float* ksrc = qkv + (size_t)m * row + (size_t)(nh + kvh) * HD;
     const float* vsrc = qkv + (size_t)m * row + (size_t)(nh + nkv + kvh) * HD;
-    float* ck = cache_k + ((size_t)m * max_ctx) * nkv * HD + (size_t)kvh * HD;
-    float* cv = cache_v + ((size_t)m * max_ctx) * nkv * HD + (size_t)kvh * HD;
     const size_t pstride = (size_t)nkv * HD;
+    // row of position j in the K / V cache of this (sequence, kv head): contiguous [max_ctx] rows, or through the block table
+    const int* bt = PAGED ? pg.block_table + (size_t)m * pg.max_blocks : nullptr;
+    auto row_of = [&](int j) -> size_t {
+        if constexpr (PAGED) return ((size_t)bt[j / pg.block_size] * pg.block_size + (size_t)(j % pg.block_size)) * pstride + (size_t)kvh * HD;
+        else return ((size_t)m * max_ctx + (size_t)j) * pstride + (size_t)kvh * HD;
+    };
+    float* ck = cache_k;
+    float* cv = cache_v;
     const float* rt = rope + (size_t)p * HD;  // [hd/2][2]
 
     __shared__ __align__(16) float sq[HD], sk[HD], sv[HD];
@@ -247,12 +270,12 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
         const int j = t >> 2;
         if (j < p) {
 #pragma unroll
-            for (int e = 0; e < QE / 4; e++) kpre[e] = *reinterpret_cast<const float4*>(ck + (size_t)j * pstride + part * QE + 4 * e);
+            for (int e = 0; e < QE / 4; e++) kpre[e] = *reinterpret_cast<const float4*>(ck + row_of(j) + part * QE + 4 * e);
         }
 #pragma unroll
         for (int it = 0; it < VPF; it++) {
             const int jv = jg + it * JG;
-            if (jv < p) vpre[it] = *reinterpret_cast<const float4*>(cv + (size_t)jv * pstride + 4 * eg);
+            if (jv < p) vpre[it] = *reinterpret_cast<const float4*>(cv + row_of(jv) + 4 * eg);
         }
         if (t < HD / 2) { rc = rt[2 * t]; rs = rt[2 * t + 1]; }
     }
@@ -271,8 +294,12 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
         sk[2 * t] = r0; sk[2 * t + 1] = r1;
         sv[2 * t] = vsrc[2 * t]; sv[2 * t + 1] = vsrc[2 * t + 1];
         if (head % (nh / nkv) == 0) {  // one head of each kv group appends the new k, v
-            ck[(size_t)p * pstride + 2 * t] = r0; ck[(size_t)p * pstride + 2 * t + 1] = r1;
-            cv[(size_t)p * pstride + 2 * t] = vsrc[2 * t]; cv[(size_t)p * pstride + 2 * t + 1] = vsrc[2 * t + 1];
+            size_t wrow = row_of(p);
+            if constexpr (PAGED) {
+                if (pg.slot_mapping) wrow = (size_t)pg.slot_mapping[m] * pstride + (size_t)kvh * HD;   // the scheduler's slot (batch_decode.rs:84-90)
+            }
+            ck[wrow + 2 * t] = r0; ck[wrow + 2 * t + 1] = r1;
+            cv[wrow + 2 * t] = vsrc[2 * t]; cv[wrow + 2 * t + 1] = vsrc[2 * t + 1];
         }
     }
     __syncthreads();
@@ -284,7 +311,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
             const int j = j0 + (t >> 2);
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
             if (j <= p) {
-                const float* kr = (j < p) ? ck + (size_t)j * pstride + part * QE : sk + part * QE;  // the new key comes from smem
+                const float* kr = (j < p) ? ck + row_of(j) + part * QE : sk + part * QE;  // the new key comes from smem
                 const float* qq = sq + part * QE;
 #pragma unroll
                 for (int e = 0; e < QE; e += 4) {
@@ -340,7 +367,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
         }
         for (int j = jg + VPF * JG; j <= p; j += JG) {
             const float pj = s_sc[j];
-            const float4 vv = (j < p) ? *reinterpret_cast<const float4*>(cv + (size_t)j * pstride + 4 * eg) : *reinterpret_cast<const float4*>(sv + 4 * eg);
+            const float4 vv = (j < p) ? *reinterpret_cast<const float4*>(cv + row_of(j) + 4 * eg) : *reinterpret_cast<const float4*>(sv + 4 * eg);
             o0 = fma((double)pj, (double)vv.x, o0); o1 = fma((double)pj, (double)vv.y, o1);
             o2 = fma((double)pj, (double)vv.z, o2); o3 = fma((double)pj, (double)vv.w, o3);
         }
@@ -461,6 +488,19 @@ __global__ void __launch_bounds__(1024) argmax_gathered_kernel(const CommDev c, 
     }
 }
 
+// MoE combine: out[t, h] = sum_j gate_w[t, j] * y[t * top_k + j, h], j ascending, separate f32 multiply and add (no FMA): the
+// order is part of the contract so the expert-parallel partial sums of different ranks are reproducible.
+__global__ void __launch_bounds__(256) moe_combine_kernel(const float* __restrict__ y, const float* __restrict__ gate_w, int top_k, int H, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = blockIdx.y;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    float acc = 0.0f;
+    for (int j = 0; j < top_k; j++) acc = __fadd_rn(acc, __fmul_rn(gate_w[(size_t)t * top_k + j], y[((size_t)t * top_k + j) * H + h]));
+    out[(size_t)t * H + h] = acc;
+}
+
 // embedding gather: h[m, :] = table[ids[m], :] (f16 table -> f32)
 // First kernel of a decode step: it releases its dependents only AFTER its own dependency wait, which breaks the
 // programmatic chain at the step boundary -- nothing of step s+1 (in particular the attention prologue, which reads
@@ -543,7 +583,7 @@ int32_t b200q_argmax_gathered(b200q_comm* comm, int64_t vs, int64_t M, int64_t* 
 int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq, void* stream) {
     if (!gate_up || !xq || F <= 0 || F % 32 || M <= 0 || M > 65535) return B200Q_ERR_INVALID_ARG;
     cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)((F + CHUNK_K - 1) / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
-                               (int)M, (uint8_t*)xq, (float*)nullptr);
+                               (int)M, (uint8_t*)xq, (float*)nullptr, 0);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }
 
@@ -551,7 +591,16 @@ int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq,
 int32_t b200q_swiglu_f32(const float* gate_up, int64_t F, int64_t M, float* act, void* stream) {
     if (!gate_up || !act || F <= 0 || F % 32 || M <= 0 || M > 65535) return B200Q_ERR_INVALID_ARG;
     cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)((F + CHUNK_K - 1) / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
-                               (int)M, (uint8_t*)nullptr, act);
+                               (int)M, (uint8_t*)nullptr, act, 0);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+/* same for a gate|up output whose columns are in the SwiGLU-epilogue row order of the weight (b200q_gate_up_row): the M > 4
+ * paths (prefill, batched decode) of a model whose gate|up weight is uploaded interleaved for the fused decode epilogue */
+int32_t b200q_swiglu_f32_interleaved(const float* gate_up, int64_t F, int64_t M, float* act, void* stream) {
+    if (!gate_up || !act || F <= 0 || F % 64 || M <= 0 || M > 65535) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(swiglu_quant_kernel, dim3((unsigned)((F + CHUNK_K - 1) / CHUNK_K), (unsigned)M), dim3(256), 0, (cudaStream_t)stream, gate_up, (int)F,
+                               (int)M, (uint8_t*)nullptr, act, 1);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }
 
@@ -564,14 +613,47 @@ int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, 
     cudaError_t e;
     dim3 grid((unsigned)n_heads, (unsigned)M);
     size_t smem = (size_t)max_ctx * sizeof(float);
+    const PagedKv none{nullptr, nullptr, 0, 0};
     if (head_dim == 128) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = launch_pdl(attn_decode_kernel<128>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
-                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = launch_pdl(attn_decode_kernel<128, false>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
+                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out, (const PagedKv)none);
     } else if (head_dim == 64) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = launch_pdl(attn_decode_kernel<64>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
-                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = launch_pdl(attn_decode_kernel<64, false>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, cache_k, cache_v, rope_table,
+                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out, (const PagedKv)none);
+    } else {
+        return B200Q_ERR_UNSUPPORTED;
+    }
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+/* Paged form (reference forward_with_paged_kv_cache, src/engine/batch_decode.rs:115-147): k_pool / v_pool are
+ * [num_blocks][block_size][nkv][hd] f32 pools shared by all sequences, block_table int32 [M][max_blocks] (padding entries are
+ * never read: only blocks below pos[m] / block_size are), slot_mapping int32 [M] = block * block_size + offset of the NEW
+ * token (nullable: derived from block_table and pos).  pos[m] = sequence length - 1.  A slot of -1 or a position >=
+ * max_blocks * block_size writes nothing and raises the sticky device error (b200q_decode_error). */
+int32_t b200q_attn_decode_paged(const float* qkv, const int32_t* pos, float* k_pool, float* v_pool, const int32_t* block_table, const int32_t* slot_mapping,
+                                int32_t block_size, int32_t max_blocks, const float* rope_table, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                                int64_t M, void* xq, float* attn_out, void* stream) {
+    if (!qkv || !pos || !k_pool || !v_pool || !block_table || !rope_table || (!xq && !attn_out) || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || M <= 0 ||
+        block_size <= 0 || max_blocks <= 0)
+        return B200Q_ERR_INVALID_ARG;
+    if (((int64_t)n_heads * head_dim) % CHUNK_K) return B200Q_ERR_INVALID_ARG;
+    const int64_t max_ctx = (int64_t)block_size * max_blocks;
+    if ((size_t)max_ctx * 4 > 160 * 1024) return B200Q_ERR_UNSUPPORTED;
+    cudaError_t e;
+    dim3 grid((unsigned)n_heads, (unsigned)M);
+    size_t smem = (size_t)max_ctx * sizeof(float);
+    const PagedKv pg{block_table, slot_mapping, block_size, max_blocks};
+    if (head_dim == 128) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = launch_pdl(attn_decode_kernel<128, true>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, k_pool, v_pool, rope_table,
+                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out, (const PagedKv)pg);
+    } else if (head_dim == 64) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = launch_pdl(attn_decode_kernel<64, true>, grid, dim3(ATT_NT), smem, (cudaStream_t)stream, qkv, (const int*)pos, k_pool, v_pool, rope_table,
+                       (int)n_heads, (int)n_kv_heads, (int)max_ctx, (int)M, (uint8_t*)xq, attn_out, (const PagedKv)pg);
     } else {
         return B200Q_ERR_UNSUPPORTED;
     }
@@ -595,6 +677,13 @@ int32_t b200q_decode_error(int32_t* out_flags) {
 int32_t b200q_argmax(const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream) {
     if (!logits || !out_ids || V <= 0 || M <= 0) return B200Q_ERR_INVALID_ARG;
     cudaError_t e = launch_pdl(argmax_kernel, dim3((unsigned)M), dim3(1024), 0, (cudaStream_t)stream, logits, (int)V, out_ids, (int*)pos_inc);
+    return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
+}
+
+/* MoE decode combine (after the grouped down projection): out[T, H] = sum over the top_k slots of gate_w[t, j] * y[t * top_k + j, :] */
+int32_t b200q_moe_combine(const float* y, const float* gate_w, int64_t T, int64_t top_k, int64_t H, float* out, void* stream) {
+    if (!y || !gate_w || !out || T <= 0 || T > 65535 || top_k <= 0 || H <= 0) return B200Q_ERR_INVALID_ARG;
+    cudaError_t e = launch_pdl(moe_combine_kernel, dim3((unsigned)((H + 255) / 256), (unsigned)T), dim3(256), 0, (cudaStream_t)stream, y, gate_w, (int)top_k, (int)H, out);
     return e == cudaSuccess ? B200Q_OK : B200Q_ERR_CUDA;
 }
 

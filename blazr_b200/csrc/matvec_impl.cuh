@@ -684,15 +684,12 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             uint8_t* mine = p.comm.peers[p.comm.rank];
             const bool ar = p.rp_mode == RP_ALLREDUCE;
             unsigned int* done = reinterpret_cast<unsigned int*>(mine + (ar ? COMM_OFF_AR_DONE : COMM_OFF_AG_DONE));
-            __threadfence_system();  // the CTA's peer stores (ordered before this thread by the barrier) are performed system-wide
+            asm volatile("fence.acq_rel.sys;" ::: "memory");  // the CTA's peer stores (ordered before this thread by the barrier) are performed system-wide
             unsigned int old;
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
             if (old == (unsigned int)(G - 1)) {
                 *done = 0u;  // next launch (ordered after this one by the stream)
-                const int par = ar ? (int)(rp.epoch & 1u) : 0;
-                const int foff = ar ? COMM_OFF_AR_FLAGS : COMM_OFF_AG_FLAGS;
-                for (int r = 0; r < p.comm.world; r++)
-                    st_release_sys(reinterpret_cast<unsigned int*>(p.comm.peers[r] + foff) + par * COMM_MAX_WORLD + p.comm.rank, rp.epoch);
+                comm_raise_flags(p.comm, ar ? COMM_OFF_AR_FLAGS : COMM_OFF_AG_FLAGS, ar ? (int)(rp.epoch & 1u) : 0, rp.epoch);
                 *reinterpret_cast<unsigned int*>(mine + (ar ? COMM_OFF_AR_EPOCH : COMM_OFF_AG_EPOCH)) = rp.epoch;
             }
         }

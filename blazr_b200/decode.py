@@ -184,12 +184,19 @@ class Decoder:
     random blocks generated on the device (bench)."""
 
     def __init__(self, client: ops.B200Client, cfg: ModelConfig, scheme: str, batch: int = 1, max_ctx: int = 512,
-                 host: Optional[HostModel] = None, seed: int = 0xB200, tp_rank: int = 0, tp_world: int = 1, group=None):
+                 host: Optional[HostModel] = None, seed: int = 0xB200, tp_rank: int = 0, tp_world: int = 1, group=None,
+                 paged: bool = False, block_size: int = 16):
+        """paged: KV cache as block pools + block table (reference InferenceConfig.paged_attention / block_size = 16,
+        src/config/inference.rs:94-98; forward_with_paged_kv_cache, src/engine/batch_decode.rs:137-147) instead of one
+        contiguous [max_ctx] region per sequence.  The block table is pre-populated with a shuffled assignment of the pool's
+        blocks; a scheduler may overwrite `block_table` / `slot_mapping` between steps (blazr_b200/batch.py builds them)."""
         assert 1 <= batch <= 256
         # M <= 4: dp4a matvec on int8 activation records (bit-exact contract); M > 4 (batched decode, reference
         # src/engine/batch_decode.rs:115-147): tcgen05 dequant-GEMM on f32 activations (1e-2 tolerance contract)
         self.wide = batch > 4
         assert not (self.wide and tp_world > 1), "batched decode is single-GPU in this round"
+        if paged:
+            max_ctx = -(-max_ctx // block_size) * block_size   # whole blocks
         self.c, self.cfg, self.scheme, self.M, self.max_ctx = client, cfg, scheme, batch, max_ctx
         self.rank, self.world, self.group = tp_rank, tp_world, group
         dev = client.device
@@ -231,8 +238,13 @@ class Decoder:
             mn = host.layers[i]["mlp_norm"] if host else np.ones(H, np.float32)
             lay["attn_norm"] = torch.from_numpy(an).to(dev)
             lay["mlp_norm"] = torch.from_numpy(mn).to(dev)
-            lay["ck"] = torch.zeros((M, max_ctx, self.nkv, hd), dtype=torch.float32, device=dev)
-            lay["cv"] = torch.zeros((M, max_ctx, self.nkv, hd), dtype=torch.float32, device=dev)
+            if paged:  # block pools [num_blocks][block_size][nkv][hd]
+                nblk = M * (-(-max_ctx // block_size))
+                lay["ck"] = torch.zeros((nblk, block_size, self.nkv, hd), dtype=torch.float32, device=dev)
+                lay["cv"] = torch.zeros((nblk, block_size, self.nkv, hd), dtype=torch.float32, device=dev)
+            else:
+                lay["ck"] = torch.zeros((M, max_ctx, self.nkv, hd), dtype=torch.float32, device=dev)
+                lay["cv"] = torch.zeros((M, max_ctx, self.nkv, hd), dtype=torch.float32, device=dev)
             self.layers.append(lay)
         self.final_norm = torch.from_numpy(host.final_norm if host else np.ones(H, np.float32)).to(dev)
         self.rope = torch.from_numpy(rope_table(max_ctx, hd, cfg.rope_theta)).to(dev)
@@ -261,6 +273,13 @@ class Decoder:
             self.logits = torch.zeros((tp_world, M, vs), **f32)
         self.ids = torch.zeros(M, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(M, dtype=torch.int32, device=dev)
+        self.paged, self.block_size = paged, block_size
+        if paged:
+            self.max_blocks = -(-max_ctx // block_size)
+            self.max_ctx = self.max_blocks * block_size
+            perm = np.random.Generator(np.random.PCG64(seed + 99)).permutation(M * self.max_blocks).astype(np.int32)
+            self.block_table = torch.from_numpy(perm.reshape(M, self.max_blocks)).to(dev)
+            self.slot_mapping = None   # int32 [M] device tensor when a scheduler provides the slots; else derived from block_table / pos
         if self.wide:
             self.xq_h, self.xq_attn, self.xq_ff = (torch.zeros((M, k), **f32) for k in (H, self.qd, self.ff))  # f32 activations
         else:
@@ -486,6 +505,42 @@ class Decoder:
         if self.world > 1:
             torch.distributed.all_reduce(t, group=self.group)
 
+    def _attention(self, lay, st):
+        """RoPE + KV append + single-query attention + output quantise (contiguous or paged KV cache)"""
+        L, cfg, M = ops.lib(), self.cfg, self.M
+        P = lambda t: C.c_void_p(t.data_ptr())
+        xq, ao = (None, P(self.xq_attn)) if self.wide else (P(self.xq_attn), None)
+        if self.paged:
+            ops._check(L.b200q_attn_decode_paged(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.block_table),
+                                                 P(self.slot_mapping) if self.slot_mapping is not None else None, C.c_int32(self.block_size),
+                                                 C.c_int32(self.max_blocks), P(self.rope), C.c_int32(self.nh), C.c_int32(self.nkv),
+                                                 C.c_int32(cfg.head_dim), C.c_int64(M), xq, ao, st))
+        else:
+            ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
+                                           C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M), xq, ao, st))
+
+    def kv_rows(self, lay, seq: int, S: int):
+        """(K, V) rows [S, nkv, hd] of positions 0..S-1 of sequence `seq`, whatever the cache layout"""
+        if not self.paged:
+            return lay["ck"][seq, :S], lay["cv"][seq, :S]
+        j = torch.arange(S, device=self.dev)
+        idx = self.block_table[seq, j // self.block_size].long() * self.block_size + j % self.block_size
+        nkv, hd = self.nkv, self.cfg.head_dim
+        return lay["ck"].view(-1, nkv, hd)[idx], lay["cv"].view(-1, nkv, hd)[idx]
+
+    def _kv_write(self, lay, seq: int, k: torch.Tensor, v: torch.Tensor):
+        """prefill: store K (rotated) / V rows [S, nkv, hd] of sequence `seq`"""
+        S = k.shape[0]
+        if not self.paged:
+            lay["ck"][seq, :S].copy_(k)
+            lay["cv"][seq, :S].copy_(v)
+            return
+        j = torch.arange(S, device=self.dev)
+        idx = self.block_table[seq, j // self.block_size].long() * self.block_size + j % self.block_size
+        nkv, hd = self.nkv, self.cfg.head_dim
+        lay["ck"].view(-1, nkv, hd)[idx] = k
+        lay["cv"].view(-1, nkv, hd)[idx] = v
+
     def _advance(self):
         """host-side mirror of the device position counter: every step (eager or replayed) passes through here, so a
         sequence can never run past the KV cache / RoPE table (the kernel guards too: b200q_decode_error)"""
@@ -548,9 +603,7 @@ class Decoder:
             else:
                 norm(lay["attn_norm"])
                 self._matvec(lay["qkv"], self.xq_h, self.qkv)
-            ops._check(L.b200q_attn_decode(P(self.qkv), P(self.pos), P(lay["ck"]), P(lay["cv"]), P(self.rope), C.c_int32(self.nh),
-                                           C.c_int32(self.nkv), C.c_int32(cfg.head_dim), C.c_int32(self.max_ctx), C.c_int64(M),
-                                           None if self.wide else P(self.xq_attn), P(self.xq_attn) if self.wide else None, st))
+            self._attention(lay, st)
             in_flight = self._rowpar(lay["o"], self.xq_attn, self.delta)
             delta = self.delta
             if lay["swiglu_epi"]:
@@ -643,6 +696,101 @@ class Decoder:
         torch.cuda.synchronize(self.dev)
         self.graph = g
         return g
+
+    # ---- prefill: one M = S pass over the prompt (reference src/engine/executor_generate.rs:357, batch_engine.rs:172-272) ----
+    def prefill(self, prompt, seq: int = 0) -> torch.Tensor:
+        """prompt: int64 [S] token ids of sequence `seq`.  Runs every projection ONCE at M = S on the tcgen05 dequant-GEMM
+        (b200q_matmul, f32 activations -> f16 tiles, f32 accumulate), fills the KV cache rows [0, S) of that sequence, leaves
+        pos[seq] = S and ids[seq] = the greedy next token, and returns the f32 logits [vocab] of the last position.  RoPE and
+        the causal attention of the prompt run in torch (SDPA, f16) -- they are not the graded path; norms,
+        SwiGLU and all 7L+1 projections are libb200q kernels.  Tolerance contract: 1e-2 relative on the logits against the f32
+        CPU path (the GEMM path quantises weights and activations to f16 tiles)."""
+        import torch.nn.functional as Fnn
+        cfg, L = self.cfg, ops.lib()
+        ids_h = np.asarray(prompt, dtype=np.int64).reshape(-1)
+        S = int(ids_h.shape[0])
+        if S < 1 or S > self.max_ctx:
+            raise ValueError(f"prompt length {S} outside [1, max_ctx={self.max_ctx}]")
+        assert 0 <= seq < self.M
+        H, hd, nh, nkv, ff = cfg.hidden, cfg.head_dim, self.nh, self.nkv, self.ff
+        dev = self.dev
+        st = ops._stream_ptr(dev)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        f32 = dict(dtype=torch.float32, device=dev)
+        b = getattr(self, "_pf", None)
+        if b is None or b["S"] != S:
+            ws_bytes = max(ln.w.workspace_bytes(S) for lay in self.layers for key in ("qkv", "o", "gu", "down") for ln in lay[key])
+            b = dict(S=S, h=torch.empty((S, H), **f32), h2=torch.empty((S, H), **f32), xn=torch.empty((S, H), **f32),
+                     qkv=torch.empty((S, self.qd + 2 * self.kvd), **f32), attn=torch.empty((S, self.qd), **f32), delta=torch.empty((S, H), **f32),
+                     delta2=torch.empty((S, H), **f32), gu=torch.empty((S, 2 * ff), **f32), act=torch.empty((S, ff), **f32),
+                     ws=torch.zeros(max(256, ws_bytes), dtype=torch.uint8, device=dev))
+            b["xq1"] = torch.zeros(int(L.b200q_act_bytes(C.c_int64(H), C.c_int64(1))), dtype=torch.uint8, device=dev)
+            b["h1"] = torch.empty((1, H), **f32)
+            b["logits1"] = torch.full((1, self.logits_local.shape[1]), float("-inf"), **f32)
+            self._pf = b
+        ids_d = torch.from_numpy(ids_h).to(dev)
+        ops._check(L.b200q_embed(P(self.embed), P(ids_d), C.c_int64(H), C.c_int64(S), P(b["h"]), st))
+        hin, hout = b["h"], b["h2"]
+        delta = None
+        rope = self.rope[:S]                                   # [S, hd/2, 2]
+        cos, sin = rope[:, None, :, 0], rope[:, None, :, 1]    # [S, 1, hd/2]
+
+        def gemm(lins, x, out):
+            for ln in lins:
+                ops._check(L.b200q_matmul(ln.w.handle, P(x), C.c_int32(ops.F32), C.c_int64(S), C.c_int64(x.stride(0)),
+                                          C.c_void_p(out.data_ptr() + 4 * ln.col0), C.c_int32(ops.F32), C.c_int64(out.stride(0)), P(b["ws"]),
+                                          C.c_size_t(b["ws"].numel()), st))
+
+        def norm(w):
+            nonlocal hin, hout
+            ops._check(L.b200q_add_rmsnorm_quant(P(hin), P(delta) if delta is not None else None, P(hout), P(w), C.c_float(cfg.eps), C.c_int64(H),
+                                                 C.c_int64(S), None, P(b["xn"]), st))
+            hin, hout = hout, hin
+
+        def rot(x):  # adjacent-pair RoPE, same table as the decode kernel
+            x2 = x.reshape(S, -1, hd // 2, 2)
+            x0, x1 = x2[..., 0], x2[..., 1]
+            return torch.stack((x0 * cos - x1 * sin, x0 * sin + x1 * cos), dim=-1).reshape(S, -1, hd)
+
+        for lay in self.layers:
+            norm(lay["attn_norm"])
+            gemm(lay["qkv"], b["xn"], b["qkv"])
+            q = rot(b["qkv"][:, :self.qd])
+            k = rot(b["qkv"][:, self.qd:self.qd + self.kvd])
+            v = b["qkv"][:, self.qd + self.kvd:].reshape(S, nkv, hd)
+            self._kv_write(lay, seq, k, v)
+            o = Fnn.scaled_dot_product_attention(q.permute(1, 0, 2)[None].half(), k.permute(1, 0, 2)[None].half(), v.permute(1, 0, 2)[None].half(),
+                                                 is_causal=True, enable_gqa=(nh != nkv))
+            b["attn"].copy_(o[0].permute(1, 0, 2).reshape(S, self.qd))
+            gemm(lay["o"], b["attn"], b["delta"])
+            if self.world > 1:
+                torch.distributed.all_reduce(b["delta"], group=self.group)   # prefill-size message: NCCL over NVLink
+            delta = b["delta"]
+            norm(lay["mlp_norm"])
+            gemm(lay["gu"], b["xn"], b["gu"])
+            sw = L.b200q_swiglu_f32_interleaved if lay["swiglu_epi"] else L.b200q_swiglu_f32
+            ops._check(sw(P(b["gu"]), C.c_int64(ff), C.c_int64(S), P(b["act"]), st))
+            gemm(lay["down"], b["act"], b["delta2"])
+            if self.world > 1:
+                torch.distributed.all_reduce(b["delta2"], group=self.group)
+            delta = b["delta2"]
+        # last position only: final norm + quantise -> lm_head on the decode matvec (M = 1) -> greedy token
+        last_h, last_d = hin[S - 1:S], delta[S - 1:S]
+        ops._check(L.b200q_add_rmsnorm_quant(P(last_h), P(last_d), P(b["h1"]), P(self.final_norm), C.c_float(cfg.eps), C.c_int64(H), C.c_int64(1),
+                                             P(b["xq1"]), None, st))
+        for ln in self.head:
+            ops._check(L.b200q_matmul_q8(ln.w.handle, P(b["xq1"]), C.c_int64(1), C.c_void_p(b["logits1"].data_ptr() + 4 * ln.col0), C.c_int32(ops.F32),
+                                         C.c_int64(b["logits1"].stride(0)), P(ln.ws), C.c_size_t(ln.ws.numel()), st))
+        logits = b["logits1"][0]
+        if self.world > 1:
+            parts = [torch.empty_like(b["logits1"]) for _ in range(self.world)]
+            torch.distributed.all_gather(parts, b["logits1"], group=self.group)
+            logits = torch.cat([p_[0] for p_ in parts])
+        logits = logits[:cfg.vocab]
+        self.ids[seq] = torch.argmax(logits)
+        self.pos[seq] = S
+        self._host_pos = max(self._host_pos, S)
+        return logits
 
     def reset(self, first_ids):
         self.ids.copy_(torch.as_tensor(first_ids, dtype=torch.int64, device=self.dev).reshape(self.M))

@@ -399,8 +399,10 @@ def moe_mlp_from_gguf(client, g: Gguf, layer: int):
     p = f"blk.{layer}."
     hidden, ffn, _ = g.tensor_info(p + "ffn_gate_exps.weight").shape
     experts = []
+    il = ffn % 64 == 0   # gate|up rows in the SwiGLU-epilogue order: the grouped gate|up launch activates and quantises too
+    order = ops.gate_up_row_order(ffn) if il else None
     for gu_blocks, gt, dn_blocks, dt in host_experts_from_gguf(g, layer):
-        gu = client.weight_from_ggml(gt, np.ascontiguousarray(gu_blocks), 2 * ffn, hidden)
+        gu = client.weight_from_ggml(gt, np.ascontiguousarray(gu_blocks[order] if il else gu_blocks), 2 * ffn, hidden)
         dn = client.weight_from_ggml(dt, np.ascontiguousarray(dn_blocks), hidden, ffn)
-        experts.append(ops.ExpertWeights(gu, dn))
+        experts.append(ops.ExpertWeights(gu, dn, interleaved=il))
     return ops.MoeMlp(client, experts, ffn, hidden)

@@ -50,15 +50,15 @@ class WeightInfo(C.Structure):
 # every symbol include/b200q.h declares (tests check the library exports each one)
 EXPORTS = [
     "b200q_version", "b200q_last_error", "b200q_device_count", "b200q_weight_from_ggml", "b200q_weight_from_ggml_shard",
-    "b200q_weight_from_awq", "b200q_weight_from_gptq", "b200q_weight_from_awq_shard", "b200q_weight_free", "b200q_weight_info",
+    "b200q_weight_from_awq", "b200q_weight_from_gptq", "b200q_weight_from_awq_shard", "b200q_weight_from_gptq_shard", "b200q_weight_free", "b200q_weight_info",
     "b200q_weight_set_bias", "b200q_weight_set_next", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
-    "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode",
+    "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode", "b200q_attn_decode_paged",
     "b200q_argmax", "b200q_decode_error", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
-    "b200q_swiglu_f32", "b200q_gate_up_row", "b200q_matmul_q8_swiglu", "b200q_matmul_norm_swiglu", "b200q_moe_matmul_q8_swiglu", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq", "b200q_program_add_attn", "b200q_program_add_argmax", "b200q_program_add_embed",
+    "b200q_swiglu_f32", "b200q_swiglu_f32_interleaved", "b200q_gate_up_row", "b200q_matmul_q8_swiglu", "b200q_matmul_norm_swiglu", "b200q_moe_matmul_q8_swiglu", "b200q_program_create", "b200q_program_add_normq", "b200q_program_add_matvec", "b200q_program_add_swigluq", "b200q_program_add_attn", "b200q_program_add_argmax", "b200q_program_add_embed",
     "b200q_program_finalize", "b200q_program_launch", "b200q_program_free", "b200q_comm_create", "b200q_comm_handle", "b200q_comm_connect", "b200q_allreduce_f64", "b200q_comm_free", "b200q_comm_gather_ptr",
     "b200q_matmul_q8_rowpar", "b200q_allreduce_add_rmsnorm_quant", "b200q_allreduce_finish", "b200q_matmul_q8_gather", "b200q_argmax_gathered", "b200q_allreduce",
-    "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8",
+    "b200q_bank_create", "b200q_bank_free", "b200q_bank_set", "b200q_bank_get", "b200q_bank_workspace_bytes", "b200q_moe_matmul_q8", "b200q_moe_combine",
 ]
 
 _lib = None
@@ -222,14 +222,14 @@ class B200Client:
                                                          C.c_int64(K), C.c_int64(n0), C.c_int64(n1), C.c_int64(k0), C.c_int64(k1),
                                                          C.c_int32(self.index), _stream_ptr(self.device), C.byref(h)))
             elif t.method.kind == "gptq":
-                if rows is not None or cols is not None:
-                    raise B200QError(-2, "GPTQ shards are built by slicing the source tensors before upload")
                 qz, _, k3_ = _src(t.qzeros)
                 gi, _, k4_ = _src(np.asarray(t.g_idx, dtype=np.int32)) if t.g_idx is not None else (None, 0, None)
                 bi, _, k5_ = _src(np.asarray(t.bias, dtype=np.float32)) if t.bias is not None else (None, 0, None)
-                _check(lib().b200q_weight_from_gptq(qw, sc, qz, gi, bi, C.c_int32(on_dev), C.c_int32(t.method.group_size),
-                                                    C.c_int32(t.zero_plus_one), C.c_int64(N), C.c_int64(K), C.c_int32(self.index),
-                                                    _stream_ptr(self.device), C.byref(h)))
+                n0, n1 = rows if rows is not None else (0, N)
+                k0, k1 = cols if cols is not None else (0, K)
+                _check(lib().b200q_weight_from_gptq_shard(qw, sc, qz, gi, bi, C.c_int32(on_dev), C.c_int32(t.method.group_size),
+                                                          C.c_int32(t.zero_plus_one), C.c_int64(N), C.c_int64(K), C.c_int64(n0), C.c_int64(n1),
+                                                          C.c_int64(k0), C.c_int64(k1), C.c_int32(self.index), _stream_ptr(self.device), C.byref(h)))
             else:
                 raise B200QError(-2, f"unknown decomposed method {t.method.kind}")
         return QuantWeight(h, self.device)
@@ -359,9 +359,11 @@ class ExpertBank:
 @dataclass
 class ExpertWeights:
     """mirror of boostr::ExpertWeights (reference src/engine/executor_cache.rs:19,344-348): one expert's projections.
-    gate_up is the row-fused [2 * ffn, hidden] weight (gate rows first) the decode path launches once."""
+    gate_up is the row-fused [2 * ffn, hidden] weight the decode path launches once: gate rows first, or (interleaved) in
+    the SwiGLU-epilogue row order (gate_up_row_order) so the grouped gate|up launch also activates and quantises."""
     gate_up: QuantWeight
     down_proj: QuantWeight
+    interleaved: bool = False
 
 
 class MoeMlp:
@@ -376,6 +378,9 @@ class MoeMlp:
         self.ffn, self.hidden = ffn, hidden
         self.local = list(range(self.E)) if local is None else list(local)
         self._experts = list(experts)
+        self.interleaved = all(e.interleaved for e in experts) and ffn % 64 == 0
+        assert self.interleaved or not any(e.interleaved for e in experts), "a bank mixes interleaved and plain gate|up weights"
+        self._bufs = {}
         self.gu = ExpertBank([e.gate_up for e in experts])
         self.down = ExpertBank([e.down_proj for e in experts])
 
@@ -387,18 +392,45 @@ class MoeMlp:
         self.down.set(e, w.down_proj)
         self._experts[e] = w
 
+    def _buffers(self, T: int, top_k: int, device):
+        key = (T, top_k)
+        b = self._bufs.get(key)
+        if b is None:
+            n = T * top_k
+            u8 = lambda nbytes: torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+            b = dict(xq=u8(lib().b200q_act_bytes(C.c_int64(self.hidden), C.c_int64(T))), aq=u8(lib().b200q_act_bytes(C.c_int64(self.ffn), C.c_int64(n))),
+                     gu=None if self.interleaved else torch.empty((n, 2 * self.ffn), dtype=torch.float32, device=device),
+                     y=torch.empty((n, self.hidden), dtype=torch.float32, device=device), out=torch.empty((T, self.hidden), dtype=torch.float32, device=device),
+                     ws_gu=u8(max(256, lib().b200q_bank_workspace_bytes(self.gu.handle, C.c_int64(n)))),
+                     ws_dn=u8(max(256, lib().b200q_bank_workspace_bytes(self.down.handle, C.c_int64(n)))))
+            self._bufs[key] = b
+        return b
+
     def forward_decode(self, x: torch.Tensor, sel: torch.Tensor, gate_w: torch.Tensor) -> torch.Tensor:
-        """x [T, hidden] f32, sel [T, top_k] int32 (bank-local expert indices), gate_w [T, top_k] f32 -> [T, hidden].
-        Three launches: grouped gate|up matvec, SwiGLU + quantise, grouped down matvec; the weighted combine is torch."""
+        """x [T, hidden] f32, sel [T, top_k] int32 (bank-local expert indices, -1 = not hosted here), gate_w [T, top_k] f32
+        -> [T, hidden] f32 (a view of an internal buffer: stable address, CUDA-graph capturable, no allocation after the
+        first call of a shape).  Launches: quantise, grouped gate|up with the fused SwiGLU epilogue (interleaved banks; else
+        grouped gate|up + SwiGLU), grouped down, weighted combine -- all libb200q kernels."""
         T, top_k = sel.shape
         n = T * top_k
-        xq = self.client.quantize_act(x)
-        gu = self.gu.matmul_q8(sel.reshape(-1), xq, T, top_k)                      # [n, 2 ffn]
-        aq = torch.empty(int(lib().b200q_act_bytes(C.c_int64(self.ffn), C.c_int64(n))), dtype=torch.uint8, device=x.device)
-        _check(lib().b200q_swiglu_quant(C.c_void_p(gu.data_ptr()), C.c_int64(self.ffn), C.c_int64(n), C.c_void_p(aq.data_ptr()),
-                                        _stream_ptr(x.device)))
-        y = self.down.matmul_q8(sel.reshape(-1), aq, n, 1)                           # [n, hidden]
-        return (y.reshape(T, top_k, self.hidden) * gate_w.unsqueeze(-1)).sum(dim=1)
+        L = lib()
+        P = lambda t_: C.c_void_p(t_.data_ptr())
+        st = _stream_ptr(x.device)
+        b = self._buffers(T, top_k, x.device)
+        x = x.contiguous()
+        sel_flat, gw = sel.reshape(-1), gate_w.contiguous()
+        _check(L.b200q_quantize_act(P(x), C.c_int32(F32), C.c_int64(T), C.c_int64(self.hidden), C.c_int64(self.hidden), None, P(b["xq"]), st))
+        if self.interleaved:
+            _check(L.b200q_moe_matmul_q8_swiglu(self.gu.handle, P(sel_flat), C.c_int64(n), P(b["xq"]), C.c_int64(T), C.c_int64(top_k), P(b["aq"]),
+                                                P(b["ws_gu"]), C.c_size_t(b["ws_gu"].numel()), st))
+        else:
+            _check(L.b200q_moe_matmul_q8(self.gu.handle, P(sel_flat), C.c_int64(n), P(b["xq"]), C.c_int64(T), C.c_int64(top_k), P(b["gu"]), C.c_int32(F32),
+                                         C.c_int64(2 * self.ffn), P(b["ws_gu"]), C.c_size_t(b["ws_gu"].numel()), st))
+            _check(L.b200q_swiglu_quant(P(b["gu"]), C.c_int64(self.ffn), C.c_int64(n), P(b["aq"]), st))
+        _check(L.b200q_moe_matmul_q8(self.down.handle, P(sel_flat), C.c_int64(n), P(b["aq"]), C.c_int64(n), C.c_int64(1), P(b["y"]), C.c_int32(F32),
+                                     C.c_int64(self.hidden), P(b["ws_dn"]), C.c_size_t(b["ws_dn"].numel()), st))
+        _check(L.b200q_moe_combine(P(b["y"]), P(gw), C.c_int64(T), C.c_int64(top_k), C.c_int64(self.hidden), P(b["out"]), st))
+        return b["out"]
 
 
 class Program:

@@ -115,6 +115,10 @@ int32_t b200q_weight_from_gptq(const uint32_t* qweight, const float* scales, con
 int32_t b200q_weight_from_awq_shard(const uint32_t* qweight, const float* scales, const float* zeros, int32_t src_on_device,
                                     int32_t group_size, int64_t N, int64_t K, int64_t n0, int64_t n1, int64_t k0, int64_t k1,
                                     int32_t device, void* stream, b200q_weight** out);
+/* GPTQ shard: same ranges; bias is sliced to [n0,n1).  An act-order weight (non-trivial g_idx) can be split along N only. */
+int32_t b200q_weight_from_gptq_shard(const uint32_t* qweight, const float* scales, const uint32_t* qzeros, const int32_t* g_idx, const float* bias,
+                                     int32_t src_on_device, int32_t group_size, int32_t zero_plus_one, int64_t N, int64_t K, int64_t n0, int64_t n1,
+                                     int64_t k0, int64_t k1, int32_t device, void* stream, b200q_weight** out);
 int32_t b200q_weight_free(b200q_weight* w);
 int32_t b200q_weight_info(const b200q_weight* w, b200q_weight_info_t* info);
 /* optional f32 bias [N] (device copy is made) added in every matmul epilogue */
@@ -183,6 +187,10 @@ size_t b200q_bank_workspace_bytes(const b200q_bank* b, int64_t n_slots);
 int32_t b200q_moe_matmul_q8(const b200q_bank* b, const int32_t* sel_dev, int64_t n_slots, const void* xq, int64_t x_rows,
                             int64_t x_slot_div, void* y, int32_t y_dtype, int64_t y_slot_stride, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* weighted combine of the selected experts' outputs (MoE decode): out[T, H] = sum_j gate_w[t, j] * y[t * top_k + j, :], j ascending,
+ * f32 multiply then add (fixed order: expert-parallel partial sums are reproducible) */
+int32_t b200q_moe_combine(const float* y, const float* gate_w, int64_t T, int64_t top_k, int64_t H, float* out, void* stream);
 
 /* ---- tensor-parallel exchange over NVLink peer memory, FUSED into the kernels on both sides of it (replaces the NCCL
  * all-reduce blazr's TP issues after the row-parallel o_proj / down_proj, reference src/engine/tensor_parallel.rs:125-163;
@@ -269,11 +277,21 @@ int32_t b200q_swiglu_quant(const float* gate_up, int64_t F, int64_t M, void* xq,
 /* batched decode (M > 4, tcgen05 path takes f32 activations): act[M, F] = silu(gate) * up.  The norm and attention
  * operators likewise accept xq == NULL when their f32 output (xnorm / attn_out) is requested instead. */
 int32_t b200q_swiglu_f32(const float* gate_up, int64_t F, int64_t M, float* act, void* stream);
+/* same, for gate_up columns in the SwiGLU-epilogue row order of an interleaved gate|up weight (b200q_gate_up_row) */
+int32_t b200q_swiglu_f32_interleaved(const float* gate_up, int64_t F, int64_t M, float* act, void* stream);
 /* RoPE (adjacent pairs; cos/sin from rope_table [max_ctx][hd/2][2] f32) on q and the new k, KV append at pos[m],
  * single-query attention (f64 reductions, deterministic exp), quantised output.
  * qkv[M,(nh+2nkv)*hd] f32; caches [M][max_ctx][nkv][hd] f32; attn_out (nullable) receives the f32 result */
 int32_t b200q_attn_decode(const float* qkv, const int32_t* pos, float* cache_k, float* cache_v, const float* rope_table, int32_t n_heads,
                           int32_t n_kv_heads, int32_t head_dim, int32_t max_ctx, int64_t M, void* xq, float* attn_out, void* stream);
+/* Paged-KV form (reference forward_with_paged_kv_cache + the slot_mapping / block_table tensors process_decode_batch builds,
+ * src/engine/batch_decode.rs:77-147): k_pool / v_pool are [num_blocks][block_size][nkv][hd] f32 pools shared by all sequences;
+ * block_table int32 [M][max_blocks] (entries beyond a sequence's length are never read), slot_mapping int32 [M] = block *
+ * block_size + offset of the NEW token (nullable: derived from block_table and pos); pos[m] = sequence length - 1.  Same
+ * arithmetic, bit for bit, as the contiguous form.  slot -1 / a position >= max_blocks * block_size -> b200q_decode_error. */
+int32_t b200q_attn_decode_paged(const float* qkv, const int32_t* pos, float* k_pool, float* v_pool, const int32_t* block_table, const int32_t* slot_mapping,
+                                int32_t block_size, int32_t max_blocks, const float* rope_table, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                                int64_t M, void* xq, float* attn_out, void* stream);
 /* A position pos[m] outside [0, max_ctx) makes b200q_attn_decode write nothing and raise a sticky per-device error
  * word instead of indexing past the KV cache.  b200q_decode_error reads and clears it for the current device
  * (synchronises the device: not capturable; call it after a generate loop).  bit 0 = position out of range. */

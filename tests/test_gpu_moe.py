@@ -127,3 +127,41 @@ def test_moe_mlp_decode_deepseek_v2_lite_shape(client):
         ls, lg = tp.ep_local_slots(torch.from_numpy(sel_h).cuda(), torch.from_numpy(gw_h).cuda(), e0, e1)
         total += local.forward_decode(xt, ls, lg).cpu().numpy()
     assert rel_err(total, ref) < 1e-6
+
+
+def test_moe_interleaved_banks_with_swiglu_epilogue_equal_plain_banks(client):
+    """gate|up experts uploaded in the SwiGLU-epilogue row order: the grouped gate|up launch activates and quantises itself
+    (4 launches per MoE layer instead of 5) -- same output bits as the plain banks; also under CUDA-graph replay with the
+    selection changing between replays, and with a slot masked to -1 (expert hosted by another rank)"""
+    hidden, ffn, E, top_k, T = 2048, 1408, 8, 3, 2
+    t4, t8 = synth.GGML["Q4_K"], synth.GGML["Q8_0"]
+    gub = [synth.random_ggml(t4, 2 * ffn, hidden, seed=600 + e) for e in range(E)]
+    dnb = [synth.random_ggml(t8, hidden, ffn, seed=700 + e) for e in range(E)]
+    order = ops.gate_up_row_order(ffn)
+    dn = [client.weight_from_ggml(t8, b_, hidden, ffn) for b_ in dnb]
+    plain = ops.MoeMlp(client, [ops.ExpertWeights(client.weight_from_ggml(t4, b_, 2 * ffn, hidden), d) for b_, d in zip(gub, dn)], ffn, hidden)
+    il = ops.MoeMlp(client, [ops.ExpertWeights(client.weight_from_ggml(t4, np.ascontiguousarray(b_[order]), 2 * ffn, hidden), d, interleaved=True)
+                             for b_, d in zip(gub, dn)], ffn, hidden)
+    assert il.interleaved and not plain.interleaved
+    x = torch.from_numpy(synth.random_act(T, hidden, seed=33)).cuda()
+    sel = torch.tensor([[1, 6, 3], [0, -1, 7]], dtype=torch.int32, device="cuda")
+    gw = torch.tensor([[0.5, 0.3, 0.2], [0.6, 0.0, 0.4]], dtype=torch.float32, device="cuda")
+    n0 = ops.launch_count()
+    a = plain.forward_decode(x, sel, gw).clone()
+    n1 = ops.launch_count()
+    b = il.forward_decode(x, sel, gw).clone()
+    n2 = ops.launch_count()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert (n1 - n0, n2 - n1) == (5, 4)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            out = il.forward_decode(x, sel, gw)
+    for new_sel in ([[2, 5, 4], [7, 0, 1]], [[1, 6, 3], [0, -1, 7]]):
+        sel.copy_(torch.tensor(new_sel, dtype=torch.int32))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, plain.forward_decode(x, sel, gw))
