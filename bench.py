@@ -458,6 +458,34 @@ def extras(client, cfg, scheme, pk, args):
             cfgs.append({"workload": wl, "error": repr(ex)[:200]})
         torch.cuda.empty_cache()
     out["configs"] = cfgs
+    # (1b) prefill pass: the whole prompt at M = S through all 7L+1 projections on the tcgen05 dequant-GEMM (+ torch SDPA attention)
+    pf = []
+    for wl, S in (("mistral-7b:Q6_K", 2048), ("llama-3-8b:AWQ", 4096)):
+        if time.perf_counter() - t_start > budget_s:
+            break
+        m_, s_ = wl.split(":")
+        try:
+            c_ = decode.PRESETS[m_]
+            d_ = decode.Decoder(client, c_, s_, batch=1, max_ctx=S + 16)
+            prompt = torch.randint(0, c_.vocab, (S,)).numpy()
+            d_.prefill(prompt)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 2
+            e0.record()
+            for _ in range(reps):
+                d_.prefill(prompt)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            lin_flops = 2.0 * S * sum(ln.w.N * ln.w.K for lay in d_.layers for key in ("qkv", "o", "gu", "down") for ln in lay[key])
+            pf.append({"workload": wl, "prompt_tokens": S, "ms": round(ms, 2), "prefill_tokens_per_s": round(S / (ms * 1e-3), 1),
+                       "linear_TFLOPs": round(lin_flops / (ms * 1e-3) / 1e12, 1), "frac_bf16_burst_incl_attention_and_glue": round(lin_flops / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], 3)})
+            del d_
+        except Exception as ex:
+            pf.append({"workload": wl, "error": repr(ex)[:200]})
+        torch.cuda.empty_cache()
+    out["prefill_pass"] = pf
     # (2) per-shape kernel table
     if time.perf_counter() - t_start < budget_s:
         try:

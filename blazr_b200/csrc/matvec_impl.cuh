@@ -194,6 +194,16 @@ __device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* x
     named_bar_sync(4, NT);  // records visible to every consumer warp
 }
 
+// Per-CTA globaltimer trace and the "skip the math" debug flag cost ~6 instructions per chunk in the consumer loop: they are
+// compiled in only with -DB200Q_MV_TRACE (make TRACE=1; tools/trace_matvec.py, tools/trace_step.py need that build).
+#ifdef B200Q_MV_TRACE
+#define MV_TRACE_ON(p) ((p).trace != nullptr)
+#define MV_DEBUG_SKIP(p) (((p).debug_flags & 1) != 0)
+#else
+#define MV_TRACE_ON(p) false
+#define MV_DEBUG_SKIP(p) false
+#endif
+
 // ---- output of one finished row sum: local y, or (fused TP exchange) the same element of every rank's slot ----
 struct RpState {
     unsigned int epoch;  // epoch of this exchange (previous + 1)
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t G = gridDim.x, g = blockIdx.x;
-    if (p.trace && tid == 0) {
+    if (MV_TRACE_ON(p) && tid == 0) {
         p.trace[g * 8 + 0] = globaltimer_ns();
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             for (int j = pre; j < pre + npf; j++)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(chunk_src(j)), "r"(wbytes) : "memory");
             pdl_wait();  // activations (written by the preceding kernel) are visible from here on
-            if (p.trace) p.trace[g * 8 + 4] = globaltimer_ns();
+            if (MV_TRACE_ON(p)) p.trace[g * 8 + 4] = globaltimer_ns();
             if (!PRO)
                 for (int j = 0; j < pre; j++)
                     bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, chunk_x(j), xbytes, &full[j]);
@@ -422,7 +432,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             const int reducer = nc >= 3 ? gf + 1 : gf;   // a middle contributor finishes at the very end of its life; else the first one
             if ((int)g != reducer) continue;
             const int sgf = ((p.plan32 ? (int64_t)sk_begin32((uint32_t)gf, (uint32_t)p.C, (uint32_t)G) : sk_begin(gf, p.C, G)) == tq * p.KC) ? 0 : 1;
-            if (p.trace && lane == 0) p.trace[g * 8 + 5] = globaltimer_ns();
+            if (MV_TRACE_ON(p) && lane == 0) p.trace[g * 8 + 5] = globaltimer_ns();
             const int64_t tql = GRP ? tq % p.tpw : tq;                      // tile index inside its weight
             const int64_t ybase = GRP ? (tq / p.tpw) * p.y_slot_stride : 0;  // grouped: output of slot tq / tpw
             constexpr int PASSES = 2 * MB;                       // 64 doubles (one double2 per lane) per pass
@@ -486,7 +496,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 for (int m = 0; m < p.M; m++) swiglu_tile_epilogue(p, s_yfix[m], tql, GRP ? (int)(tq / p.tpw) : m, lane);
                 __syncwarp();
             }
-            if (p.trace && lane == 0) p.trace[g * 8 + 7] = globaltimer_ns();
+            if (MV_TRACE_ON(p) && lane == 0) p.trace[g * 8 + 7] = globaltimer_ns();
         }
         if constexpr (EPI) {
             // full tiles of this CTA, in the consumers' order: wait for the tile, activate + quantise it, hand the buffer back
@@ -546,7 +556,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     int n_full_done = 0;  // OUT_SWIGLU: full tiles flushed so far (selects the s_y buffer)
     for (int j = 0; j < n_chunks; j++) {
         mbar_wait(&full[s], ph);
-        if (p.trace && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
+        if (MV_TRACE_ON(p) && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
         const uint8_t* wc = stages + (size_t)s * p.stage_bytes;
         const uint8_t* xr = PRO ? xhat + (size_t)kcur * p.M * ACT_REC_BYTES : wc + p.chunk_bytes;
         if (PRO) { if (++kcur == KC) kcur = 0; }
@@ -565,7 +575,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             bsB[m] = (int)(int16_t)(bs >> 16);
         }
         const bool skip_chunk = GRP && *reinterpret_cast<const volatile int*>(wc + p.chunk_bytes + p.M * ACT_REC_BYTES) != 0;
-        if (!(p.debug_flags & 1) && !skip_chunk)
+        if (!MV_DEBUG_SKIP(p) && !skip_chunk)
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++) {
             const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
@@ -694,7 +704,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             }
         }
     }
-    if (p.trace && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
+    if (MV_TRACE_ON(p) && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }
 
 template <class F, int MB, bool PRO, bool GRP, int OUT = OUT_PLAIN>

@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (read here with `ncu -i`, no GPU needed) into profiles/<name>.txt and update
-profiles/r1_traffic.json (per-launch DRAM bytes of the bench's roofline kernel, read by bench.py).
+profiles/r2_traffic.json (per-launch DRAM bytes of the bench's roofline kernel, read by bench.py).
 
     python tools/ncu_summary.py gpurun_out/prof_x.ncu-rep profiles/r1_x_ncu.txt "header text" [--traffic-key KEY]
 """
@@ -46,7 +46,7 @@ def main():
                    "dram_bytes_write": to_bytes(*d["dram__bytes_write.sum"]), "ncu_report": os.path.relpath(out, os.path.dirname(os.path.abspath(__file__)) + "/..")}
     open(out, "w").write("\n".join(lines))
     if key and traffic:
-        path = os.path.join(os.path.dirname(out), "r1_traffic.json")
+        path = os.path.join(os.path.dirname(out), os.environ.get("B200Q_TRAFFIC_JSON", "r2_traffic.json"))
         tj = json.load(open(path)) if os.path.exists(path) else {}
         tj[key] = traffic
         json.dump(tj, open(path, "w"), indent=1)

@@ -1,0 +1,24 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"matvec_kernel|attn_decode|add_rmsnorm|argmax|embed_kernel|swiglu" -c 900 --csv --log-file gpurun_out/r2_decode_step_launches.csv python bench.py --steps 2 --warmup 3 --no-extra > gpurun_out/r2_ncu_launches.log 2>&1
+echo "launch list rc $?"; wc -l gpurun_out/r2_decode_step_launches.csv
+cat > /tmp/gk.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from blazr_b200 import ops, synth, decode
+client = ops.B200Client(0)
+N, K, M = 14336, 4096, 2048
+ws = [client.weight_from_ggml(synth.GGML["Q6_K"], decode.random_ggml_device("Q6_K", N, K, 100 + i, client.device), N, K) for i in range(4)]
+x = torch.randn((M, K), device="cuda"); y = torch.empty((M, N), device="cuda")
+wss = [w.workspace(M) for w in ws]
+for w, s in zip(ws, wss): client.quant_matmul(x, w, out=y, workspace=s)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    for w, s in zip(ws, wss): client.quant_matmul(x, w, out=y, workspace=s)
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) * 1e3 / 20
+print(f"NX={os.environ.get('B200Q_GEMM_NX')} NW={os.environ.get('B200Q_GEMM_NW')}: {us:.1f} us  {2.0*M*N*K/(us*1e-6)/1e12:.0f} TFLOP/s")
+PY
+for cfg in "x x" "5 3" "6 2" "6 3" "7 2" "3 4"; do set -- $cfg; if [ "$1" = "x" ]; then python /tmp/gk.py 2>&1 | tail -1; else B200Q_GEMM_NX=$1 B200Q_GEMM_NW=$2 python /tmp/gk.py 2>&1 | tail -1; fi; done
