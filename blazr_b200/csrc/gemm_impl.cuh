@@ -45,13 +45,50 @@ struct GemmParams {
     int splits;        // split-K factor (serial K loop is the latency floor when there are fewer tiles than SMs)
     float* partial;    // [splits][M][N] f32 when splits > 1
     uint32_t idesc;
+    int xmc;           // 1: launched as clusters of two CTAs that work on ADJACENT weight tiles of the same activation tile; each
+                       // CTA fetches half of every activation stage and TMA-multicasts it to both (halves the L2 -> SM traffic
+                       // that bounds the wide-M kernel: 128 KB of X per 27 KB chunk of W)
 };
+
+// work item -> (weight tile t, activation tile mt, K split sp).  Plain: items = tiles, one CTA each.  xmc: items are tile
+// PAIRS (2 tp, 2 tp + 1) walked by a cluster; the odd CTA of a trailing pair recomputes tile T-1 and stores nothing.
+struct GemmItem {
+    int t, mt, sp;
+    bool valid;
+};
+__device__ __forceinline__ int gemm_first(const GemmParams& p) { return p.xmc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+__device__ __forceinline__ int gemm_stride(const GemmParams& p) { return p.xmc ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
+__device__ __forceinline__ int gemm_total(const GemmParams& p) { return (p.xmc ? (p.T + 1) / 2 : p.T) * p.MT * p.splits; }
+__device__ __forceinline__ GemmItem gemm_item(const GemmParams& p, int it) {
+    GemmItem g;
+    g.sp = it % p.splits;
+    const int rest = it / p.splits;
+    g.mt = rest % p.MT;
+    int t = rest / p.MT;
+    if (p.xmc) t = 2 * t + (int)(blockIdx.x & 1);
+    g.valid = t < p.T;
+    g.t = g.valid ? t : p.T - 1;
+    return g;
+}
 
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {  // arrive on the same barrier of every CTA in the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -141,7 +178,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < p.nw; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], GT_DQ_WARPS); }
-        for (int s = 0; s < p.nx; s++) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+        for (int s = 0; s < p.nx; s++) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], p.xmc ? 2 : 1); }  // xmc: both CTAs' MMAs release a stage
         for (int s = 0; s < p.nslots; s++) { mbar_init(&a_full[s], GT_DQ_WARPS); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4); }
         fence_mbar_init();
@@ -153,10 +190,12 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
     }
     tc_fence_before();
     __syncthreads();
+    if (p.xmc) cluster_sync_all();  // the peer's barriers exist before anything is multicast into this CTA
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
-    const int total_tiles = p.T * p.MT * p.splits;
+    const int total_tiles = gemm_total(p);
+    const int it0 = gemm_first(p), its = gemm_stride(p);
     const int KS = p.KC * 4;  // 64-k sub-stages along K
 
     if (warp == 0) {
@@ -165,8 +204,9 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
             const uint64_t pol = policy_evict_first();
             int s = 0;
             uint32_t ph = 1;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int sp_ = tile % p.splits, t = (tile / p.splits) / p.MT;
+            for (int tile = it0; tile < total_tiles; tile += its) {
+                const GemmItem gi = gemm_item(p, tile);
+                const int sp_ = gi.sp, t = gi.t;
                 const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
                 const uint8_t* src = p.w + ((size_t)t * p.KC + kc0) * p.chunk_bytes;
                 for (int kc = kc0; kc < kc1; kc++) {
@@ -184,16 +224,19 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 1;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int sp_ = tile % p.splits, mt = (tile / p.splits) % p.MT;
+            const uint32_t half = (uint32_t)p.x_stage_bytes >> 1, hoff = (uint32_t)(blockIdx.x & 1) * half;
+            for (int tile = it0; tile < total_tiles; tile += its) {
+                const GemmItem gi = gemm_item(p, tile);
+                const int sp_ = gi.sp, mt = gi.mt;
                 const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
                 // one X stage = xsub consecutive 64-k sub-tiles (contiguous in the staged layout): 1 for wide M tiles,
                 // 4 (a whole chunk) for skinny ones, where per-stage handshakes would otherwise pace the MMA issuer
                 const uint8_t* src = p.xs + ((size_t)mt * KS + 4 * kc0) * (size_t)(p.Mt * 128);
                 for (int ks = 4 * kc0; ks < 4 * kc1; ks += p.xsub) {
-                    mbar_wait(&empty_x[s], ph);
+                    mbar_wait(&empty_x[s], ph);   // xmc: BOTH CTAs have consumed this stage (their commits are multicast)
                     mbar_arrive_expect_tx(&full_x[s], (uint32_t)p.x_stage_bytes);
-                    bulk_g2s(xst + (size_t)s * p.x_stage_bytes, src, (uint32_t)p.x_stage_bytes, &full_x[s]);
+                    if (p.xmc) bulk_g2s_mc(xst + (size_t)s * p.x_stage_bytes + hoff, src + hoff, half, &full_x[s], (uint16_t)3);  // my half -> both CTAs
+                    else bulk_g2s(xst + (size_t)s * p.x_stage_bytes, src, (uint32_t)p.x_stage_bytes, &full_x[s]);
                     src += p.x_stage_bytes;
                     if (++s == p.nx) { s = 0; ph ^= 1u; }
                 }
@@ -204,8 +247,8 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         if (elect_one()) {
             int xs = 0, as = 0, acc = 0;
             uint32_t xph = 0, aph = 0, eph0 = 1, eph1 = 1;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int sp_ = tile % p.splits;
+            for (int tile = it0; tile < total_tiles; tile += its) {
+                const int sp_ = gemm_item(p, tile).sp;
                 const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
                 if (EPI) {  // the epilogue warps have drained this accumulator buffer (two items ago)
                     mbar_wait(&d_empty[acc], acc ? eph1 : eph0);
@@ -226,7 +269,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
 #pragma unroll
                             for (int kk = 0; kk < 4; kk++)
                                 tc_mma_ts(tmem + d_col, a_chunk + j * 32 + kk * 8, bdesc0 + j * sub + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
-                        tc_commit(&empty_x[xs]);
+                        if (p.xmc) tc_commit_mc(&empty_x[xs], (uint16_t)3); else tc_commit(&empty_x[xs]);
                         if (++xs == p.nx) { xs = 0; xph ^= 1u; }
                     } else {
 #pragma unroll 1
@@ -237,7 +280,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
 #pragma unroll
                             for (int kk = 0; kk < 4; kk++)
                                 tc_mma_ts(tmem + d_col, a_chunk + j * 32 + kk * 8, bdesc + (uint64_t)(kk * 2), p.idesc, ((kc - kc0) | j | kk) != 0 ? 1u : 0u);
-                            tc_commit(&empty_x[xs]);
+                            if (p.xmc) tc_commit_mc(&empty_x[xs], (uint16_t)3); else tc_commit(&empty_x[xs]);
                             if (++xs == p.nx) { xs = 0; xph ^= 1u; }
                         }
                     }
@@ -255,8 +298,9 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
         int acc = 0;
         uint32_t ph0 = 0, ph1 = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int sp_ = tile % p.splits, t = (tile / p.splits) / p.MT, mt = (tile / p.splits) % p.MT;
+        for (int tile = it0; tile < total_tiles; tile += its) {
+            const GemmItem gi = gemm_item(p, tile);
+            const int sp_ = gi.sp, t = gi.t, mt = gi.mt;
             mbar_wait(&d_full[acc], acc ? ph1 : ph0);
             if (acc) ph1 ^= 1u; else ph0 ^= 1u;
             tc_fence_after();
@@ -271,7 +315,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&d_empty[acc]);
                 }
-                if (n < p.N) {
+                if (n < p.N && gi.valid) {
 #pragma unroll
                     for (int c = 0; c < 16; c++) {
                         const int64_t m = (int64_t)mt * p.Mt + cb + c;
@@ -292,8 +336,9 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         const FmtMeta meta{p.gpc};
         int ws = 0, as = 0;
         uint32_t wph = 0, aph = 1, dph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int sp_ = tile % p.splits, t = (tile / p.splits) / p.MT, mt = (tile / p.splits) % p.MT;
+        for (int tile = it0; tile < total_tiles; tile += its) {
+            const GemmItem gi = gemm_item(p, tile);
+            const int sp_ = gi.sp, t = gi.t, mt = gi.mt;
             const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
             for (int kc = kc0; kc < kc1; kc++) {
                 mbar_wait(&full_w[ws], wph);
@@ -329,7 +374,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
                 uint32_t v[16];
                 tc_ld16(lane_base + GT_D_COL + h * half_cols + cb, v);
                 tc_wait_ld();
-                if (n < p.N) {
+                if (n < p.N && gi.valid) {
 #pragma unroll
                     for (int c = 0; c < 16; c++) {
                         const int64_t m = (int64_t)mt * p.Mt + h * half_cols + cb + c;
@@ -346,6 +391,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
 
     tc_fence_before();
     __syncthreads();
+    if (p.xmc) cluster_sync_all();  // the peer may still multicast into this CTA's stages / arrive on its barriers until it is done too
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -361,6 +407,23 @@ static cudaError_t launch_gemm_dq(const GemmParams& p, int grid, int smem, cudaS
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F, DQW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
+    }
+    if (p.xmc) {  // clusters of two CTAs (adjacent weight tiles, shared activation stages)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((4 + DQW + (EPI ? 4 : 0)) * 32);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<F, DQW, EPI>, p);
+        count_launch();
+        return le != cudaSuccess ? le : cudaGetLastError();
     }
     gemm_tc_kernel<F, DQW, EPI><<<grid, (4 + DQW + (EPI ? 4 : 0)) * 32, smem, st>>>(p);
     count_launch();

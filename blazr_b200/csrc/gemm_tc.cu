@@ -157,8 +157,15 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     p.splits = pick_splits(w, MT, M);
     p.dq_warps = Mt <= 128 ? 16 : 8;
     p.partial = reinterpret_cast<float*>(ws + (((size_t)MT * Mt * (size_t)w->K_pad * 2 + 255) & ~(size_t)255));
-    int64_t tiles = (int64_t)p.T * MT * p.splits;
+    // wide M tiles (prefill): pairs of CTAs on adjacent weight tiles can share every activation stage by TMA multicast
+    // (B200Q_GEMM_XMC=1).  Measured in round 2: correct (all GEMM parity tests, odd tile counts included) and NEUTRAL -- 862 vs 863
+    // TFLOP/s on 14336x4096xM2048, 986 vs 979 on 28672x4096 -- so the activation tile's L2 -> SM traffic is not what bounds the
+    // kernel (round 1's hypothesis); the 14336-row shape loses 14 % to wave quantisation (896 tiles on 148 SMs = 6.05 waves).  Off by default.
+    static const bool xmc_on = [] { const char* e_ = getenv("B200Q_GEMM_XMC"); return e_ && atoi(e_) != 0; }();
+    p.xmc = (xmc_on && Mt > 128 && p.xsub == 1 && w->T >= 2) ? 1 : 0;
+    int64_t tiles = (int64_t)(p.xmc ? (p.T + 1) / 2 * 2 : p.T) * MT * p.splits;
     int grid = (int)(tiles < w->num_sms ? tiles : w->num_sms);
+    if (p.xmc) grid &= ~1;
     cudaError_t ge;
     ge = gemm_launch_family(w->family, p, grid, smem, st);
     if (ge != cudaSuccess || p.splits == 1) return ge;
