@@ -45,6 +45,11 @@ struct GemmParams {
     int splits;        // split-K factor (serial K loop is the latency floor when there are fewer tiles than SMs)
     float* partial;    // [splits][M][N] f32 when splits > 1
     uint32_t idesc;
+    // tail split-K (wide M): tiles [0, tail_first) are whole work items; the tail_n tiles of the last, partial wave are cut
+    // tail_splits ways along K so that wave is short and full (896 tiles on 148 SMs otherwise run 7 waves for 6.05 waves of work);
+    // their partial accumulators go to partial_tail [tail_n][tail_splits][128][Mt] f32 and splitk_tail_reduce_kernel sums them
+    int tail_first, tail_n, tail_splits;
+    float* partial_tail;
     int xmc;           // 1: launched as clusters of two CTAs that work on ADJACENT weight tiles of the same activation tile; each
                        // CTA fetches half of every activation stage and TMA-multicasts it to both (halves the L2 -> SM traffic
                        // that bounds the wide-M kernel: 128 KB of X per 27 KB chunk of W)
@@ -53,22 +58,50 @@ struct GemmParams {
 // work item -> (weight tile t, activation tile mt, K split sp).  Plain: items = tiles, one CTA each.  xmc: items are tile
 // PAIRS (2 tp, 2 tp + 1) walked by a cluster; the odd CTA of a trailing pair recomputes tile T-1 and stores nothing.
 struct GemmItem {
-    int t, mt, sp;
+    int t, mt, sp, nsp;   // weight tile, activation tile, K split index / count of this item
+    int kc0, kc1;         // k-chunk range
+    int tail;             // >= 0: index of this tile among the tail tiles (partials go to partial_tail); -1 otherwise
     bool valid;
 };
 __device__ __forceinline__ int gemm_first(const GemmParams& p) { return p.xmc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
 __device__ __forceinline__ int gemm_stride(const GemmParams& p) { return p.xmc ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
-__device__ __forceinline__ int gemm_total(const GemmParams& p) { return (p.xmc ? (p.T + 1) / 2 : p.T) * p.MT * p.splits; }
+__device__ __forceinline__ int gemm_total(const GemmParams& p) {
+    if (p.tail_splits > 1) return p.tail_first + p.tail_n * p.tail_splits;
+    return (p.xmc ? (p.T + 1) / 2 : p.T) * p.MT * p.splits;
+}
 __device__ __forceinline__ GemmItem gemm_item(const GemmParams& p, int it) {
     GemmItem g;
-    g.sp = it % p.splits;
-    const int rest = it / p.splits;
+    int rest;
+    if (p.tail_splits > 1) {   // (splits == 1, no clusters)
+        if (it >= p.tail_first) {
+            const int r = it - p.tail_first;
+            g.tail = r / p.tail_splits;
+            g.sp = r % p.tail_splits;
+            g.nsp = p.tail_splits;
+            rest = p.tail_first + g.tail;
+        } else {
+            g.tail = -1; g.sp = 0; g.nsp = 1;
+            rest = it;
+        }
+    } else {
+        g.tail = -1;
+        g.sp = it % p.splits;
+        g.nsp = p.splits;
+        rest = it / p.splits;
+    }
     g.mt = rest % p.MT;
     int t = rest / p.MT;
     if (p.xmc) t = 2 * t + (int)(blockIdx.x & 1);
     g.valid = t < p.T;
     g.t = g.valid ? t : p.T - 1;
+    g.kc0 = g.sp * p.KC / g.nsp;
+    g.kc1 = (g.sp + 1) * p.KC / g.nsp;
     return g;
+}
+// where one accumulator element of a split item goes
+__device__ __forceinline__ float* gemm_partial_ptr(const GemmParams& p, const GemmItem& g, int r, int64_t n, int64_t m, int m_local) {
+    if (g.tail >= 0) return p.partial_tail + (((size_t)g.tail * p.tail_splits + g.sp) * TILE_ROWS + r) * p.Mt + m_local;
+    return p.partial + ((size_t)g.sp * p.M + m) * p.N + n;
 }
 
 // ---- tcgen05 wrappers ----
@@ -206,8 +239,8 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
             uint32_t ph = 1;
             for (int tile = it0; tile < total_tiles; tile += its) {
                 const GemmItem gi = gemm_item(p, tile);
-                const int sp_ = gi.sp, t = gi.t;
-                const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                const int t = gi.t;
+                const int kc0 = gi.kc0, kc1 = gi.kc1;
                 const uint8_t* src = p.w + ((size_t)t * p.KC + kc0) * p.chunk_bytes;
                 for (int kc = kc0; kc < kc1; kc++) {
                     mbar_wait(&empty_w[s], ph);
@@ -227,8 +260,8 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
             const uint32_t half = (uint32_t)p.x_stage_bytes >> 1, hoff = (uint32_t)(blockIdx.x & 1) * half;
             for (int tile = it0; tile < total_tiles; tile += its) {
                 const GemmItem gi = gemm_item(p, tile);
-                const int sp_ = gi.sp, mt = gi.mt;
-                const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                const int mt = gi.mt;
+                const int kc0 = gi.kc0, kc1 = gi.kc1;
                 // one X stage = xsub consecutive 64-k sub-tiles (contiguous in the staged layout): 1 for wide M tiles,
                 // 4 (a whole chunk) for skinny ones, where per-stage handshakes would otherwise pace the MMA issuer
                 const uint8_t* src = p.xs + ((size_t)mt * KS + 4 * kc0) * (size_t)(p.Mt * 128);
@@ -248,8 +281,8 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
             int xs = 0, as = 0, acc = 0;
             uint32_t xph = 0, aph = 0, eph0 = 1, eph1 = 1;
             for (int tile = it0; tile < total_tiles; tile += its) {
-                const int sp_ = gemm_item(p, tile).sp;
-                const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+                const GemmItem gi = gemm_item(p, tile);
+                const int kc0 = gi.kc0, kc1 = gi.kc1;
                 if (EPI) {  // the epilogue warps have drained this accumulator buffer (two items ago)
                     mbar_wait(&d_empty[acc], acc ? eph1 : eph0);
                     if (acc) eph1 ^= 1u; else eph0 ^= 1u;
@@ -300,7 +333,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         uint32_t ph0 = 0, ph1 = 0;
         for (int tile = it0; tile < total_tiles; tile += its) {
             const GemmItem gi = gemm_item(p, tile);
-            const int sp_ = gi.sp, t = gi.t, mt = gi.mt;
+            const int t = gi.t, mt = gi.mt;
             mbar_wait(&d_full[acc], acc ? ph1 : ph0);
             if (acc) ph1 ^= 1u; else ph0 ^= 1u;
             tc_fence_after();
@@ -320,7 +353,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
                     for (int c = 0; c < 16; c++) {
                         const int64_t m = (int64_t)mt * p.Mt + cb + c;
                         if (m < p.M) {
-                            if (p.splits > 1) p.partial[((size_t)sp_ * p.M + m) * p.N + n] = __uint_as_float(v[c]);
+                            if (gi.nsp > 1) *gemm_partial_ptr(p, gi, r, n, m, cb + c) = __uint_as_float(v[c]);
                             else store_out(p.y, p.y_dtype, m * p.ldy + n, __uint_as_float(v[c]) + bv);
                         }
                     }
@@ -338,8 +371,8 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         uint32_t wph = 0, aph = 1, dph = 0;
         for (int tile = it0; tile < total_tiles; tile += its) {
             const GemmItem gi = gemm_item(p, tile);
-            const int sp_ = gi.sp, t = gi.t, mt = gi.mt;
-            const int kc0 = sp_ * p.KC / p.splits, kc1 = (sp_ + 1) * p.KC / p.splits;
+            const int t = gi.t, mt = gi.mt;
+            const int kc0 = gi.kc0, kc1 = gi.kc1;
             for (int kc = kc0; kc < kc1; kc++) {
                 mbar_wait(&full_w[ws], wph);
                 const uint8_t* wc = wst + (size_t)ws * p.w_stage_bytes;
@@ -379,7 +412,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
                     for (int c = 0; c < 16; c++) {
                         const int64_t m = (int64_t)mt * p.Mt + h * half_cols + cb + c;
                         if (m < p.M) {
-                            if (p.splits > 1) p.partial[((size_t)sp_ * p.M + m) * p.N + n] = __uint_as_float(v[c]);
+                            if (gi.nsp > 1) *gemm_partial_ptr(p, gi, r, n, m, h * half_cols + cb + c) = __uint_as_float(v[c]);
                             else store_out(p.y, p.y_dtype, m * p.ldy + n, __uint_as_float(v[c]) + bv);
                         }
                     }

@@ -36,6 +36,38 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
     store_out(y, y_dtype, m * ldy + n, acc + (bias ? bias[n] : 0.0f));
 }
 
+// tail split-K reduction: y[m, n] of the tail tiles = sum over splits of partial_tail[tile][s][r][c] (+ bias), split order (deterministic)
+__global__ void splitk_tail_reduce_kernel(const float* __restrict__ partial, int tail_first, int tail_n, int S, int MT, int Mt, int64_t M, int64_t N,
+                                          const float* __restrict__ bias, void* y, int y_dtype, int64_t ldy) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, c, r) with r fastest: coalesced along n
+    const int64_t per = (int64_t)TILE_ROWS * Mt;
+    if (idx >= (int64_t)tail_n * per) return;
+    const int tl = (int)(idx / per), c = (int)((idx % per) / TILE_ROWS), r = (int)(idx % TILE_ROWS);
+    const int lin = tail_first + tl, mt = lin % MT, t = lin / MT;
+    const int64_t m = (int64_t)mt * Mt + c, n = (int64_t)t * TILE_ROWS + r;
+    if (m >= M || n >= N) return;
+    float acc = 0.0f;
+    for (int s_ = 0; s_ < S; s_++) acc += partial[(((size_t)tl * S + s_) * TILE_ROWS + r) * Mt + c];
+    store_out(y, y_dtype, m * ldy + n, acc + (bias ? bias[n] : 0.0f));
+}
+
+// tail plan of a wide-M launch: (first tail tile, tail tiles, splits); splits == 1 means "no tail split"
+static void tail_plan(const b200q_weight* w, int MT, int64_t M, int grid, int* first, int* n, int* S) {
+    *first = 0; *n = 0; *S = 1;
+    // Measured in round 2 (B200Q_GEMM_TAIL=1): correct, and 3-6 % SLOWER (14336x4096xM2048: 814 vs 864 TFLOP/s; 28672: 943 vs 992)
+    // although it removes a 7th wave that is 95 % empty -- the 8 CTAs of that wave run alone at a much higher rate, i.e. the kernel
+    // is bounded by a chip-wide resource (power / L2), not per-SM time, and the extra registers + partial traffic cost more than
+    // the idle SMs.  Kept as an opt-in experiment.
+    static const bool on = [] { const char* e_ = getenv("B200Q_GEMM_TAIL"); return e_ && atoi(e_) != 0; }();
+    const int64_t tiles = w->T * MT;
+    if (!on || M <= 128 || tiles <= grid || tiles % grid == 0) return;
+    const int rem = (int)(tiles % grid);
+    int s = grid / rem;                       // rem * s <= grid: the tail is ONE short wave
+    if (s > (int)w->KC / 2) s = (int)w->KC / 2;  // >= 2 chunks per split
+    if (s < 2) return;
+    *first = (int)(tiles - rem); *n = rem; *S = s;
+}
+
 // split-K factor: the work items (tiles x splits) should fill whole waves of the SMs.  Wide-M launches only split
 // when there are fewer tiles than SMs; skinny launches (one M tile, HBM-bound) pick the split with the least wave
 // quantisation loss, since a 112-tile weight on 148 SMs otherwise idles a quarter of the machine.
@@ -78,7 +110,9 @@ size_t gemm_ws_bytes(const b200q_weight* w, int64_t M) {
     int Mt = pick_mt(M, &MT);
     size_t xs = ((size_t)MT * Mt * (size_t)w->K_pad * 2 + 255) & ~(size_t)255;
     int S = pick_splits(w, MT, M);
-    return xs + (S > 1 ? (size_t)S * M * w->N * sizeof(float) : 0);
+    int tf, tn, ts;
+    tail_plan(w, MT, M, w->num_sms, &tf, &tn, &ts);
+    return xs + (S > 1 ? (size_t)S * M * w->N * sizeof(float) : 0) + (ts > 1 ? (size_t)tn * ts * TILE_ROWS * Mt * sizeof(float) : 0);
 }
 
 
@@ -166,8 +200,22 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     int64_t tiles = (int64_t)(p.xmc ? (p.T + 1) / 2 * 2 : p.T) * MT * p.splits;
     int grid = (int)(tiles < w->num_sms ? tiles : w->num_sms);
     if (p.xmc) grid &= ~1;
+    p.tail_first = p.tail_n = 0;
+    p.tail_splits = 1;
+    p.partial_tail = nullptr;
+    if (!p.xmc && p.splits == 1 && grid == w->num_sms) {
+        tail_plan(w, MT, M, grid, &p.tail_first, &p.tail_n, &p.tail_splits);
+        if (p.tail_splits > 1) p.partial_tail = p.partial;   // (splits == 1: the uniform split-K buffer is empty, the tail buffer starts there)
+    }
     cudaError_t ge;
     ge = gemm_launch_family(w->family, p, grid, smem, st);
+    if (ge == cudaSuccess && p.tail_splits > 1) {
+        const int64_t total_t = (int64_t)p.tail_n * TILE_ROWS * Mt;
+        splitk_tail_reduce_kernel<<<(unsigned)((total_t + 255) / 256), 256, 0, st>>>(p.partial_tail, p.tail_first, p.tail_n, p.tail_splits, MT, Mt, M, w->N, w->bias,
+                                                                                     y, y_dtype, ldy);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (ge != cudaSuccess || p.splits == 1) return ge;
     const int64_t total = M * w->N;
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.splits, M, w->N, w->bias, y, y_dtype, ldy);

@@ -91,3 +91,17 @@ def test_gemm_prefill_shape_property(client):
     rows = [0, 1, 777, 2047]
     ref = c.oracle_a(x[rows].cpu().numpy())
     assert rel_err(y[rows].cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("fmt,bias", [("Q6_K", False), ("Q4_K", False), ("GPTQ", True)])
+def test_gemm_tail_split_k_wave_quantisation(client, fmt, bias, monkeypatch):
+    """(opt-in path, B200Q_GEMM_TAIL=1 -- the switch is read once per process, so the driver's default suite exercises the plain
+    persistent loop on this shape and `B200Q_GEMM_TAIL=1 pytest -k tail_split` the split form; both were run green in round 2)
+    wide-M launch whose tile count is not a multiple of the SM count: the tiles of the last, partial wave are split along K
+    (tail split-K: 19 x 8 = 152 tiles on 148 SMs -> 4 tail tiles x 4 splits), partial accumulators reduced by a second kernel;
+    ragged M so the last activation tile is partly empty"""
+    N, K, M = 128 * 19, 2048, 2000
+    c = Case(client, fmt, N, K, seed=12, bias=bias) if bias else Case(client, fmt, N, K, seed=12)
+    x = synth.random_act(M, K, seed=5)
+    y = client.quant_matmul(torch.from_numpy(x).cuda(), c.w).cpu().numpy()
+    assert rel_err(y, c.oracle_a(x)) < TOL
