@@ -192,7 +192,11 @@ def run_b200(args):
     M = args.batch
     max_ctx = args.prompt + args.warmup + 2 * args.steps + 64
     launches0 = ops.launch_count()
-    dec = decode.Decoder(client, cfg, scheme, batch=M, max_ctx=max_ctx, tp_rank=rank, tp_world=world)
+    emu = int(os.environ.get("B200Q_EMULATE_TP", "0"))   # profiling aid: rank 0's shard of a TP-emu model alone on this GPU (world-1 exchange)
+    if emu > 1 and world == 1:
+        dec = decode.Decoder(client, cfg, scheme, batch=M, max_ctx=max_ctx, tp_rank=0, tp_world=emu, emulate_shard=True)
+    else:
+        dec = decode.Decoder(client, cfg, scheme, batch=M, max_ctx=max_ctx, tp_rank=rank, tp_world=world)
     if world > 1:
         dist.barrier()
     dec.capture()

@@ -22,7 +22,7 @@ int32_t set_error(int32_t code, const char* fmt, ...);
 
 constexpr int AR_MAX_CTAS = 32;
 
-// stand-alone all-reduce: push -> last CTA raises the flags -> every CTA waits for all ranks -> ordered f64 sum
+// stand-alone all-reduce: push (self-validating slots) -> every thread waits for all ranks' values of its elements -> ordered f64 sum
 template <typename T>
 __global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, const T* __restrict__ src, float* __restrict__ dst, int64_t n) {
     pdl_launch_dependents();
@@ -35,28 +35,12 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, const T
     const int64_t i0 = (int64_t)cta * per, i1 = min(n, i0 + per);
     const size_t off = comm_ar_slot_off(c, par, c.rank);
     for (int64_t i = i0 + tid; i < i1; i += blockDim.x) {
-        const double v = (double)src[i];
+        const double v = ar_encode((double)src[i]);
         for (int p = 0; p < c.world; p++) reinterpret_cast<double*>(c.peers[p] + off)[i] = v;
     }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int* done = reinterpret_cast<unsigned int*>(mine + COMM_OFF_AR_DONE);
-        asm volatile("fence.acq_rel.sys;" ::: "memory");
-        unsigned int old;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
-        if (old == (unsigned int)(G - 1)) {
-            *done = 0u;
-            comm_raise_flags(c, COMM_OFF_AR_FLAGS, par, epoch);
-            *reinterpret_cast<unsigned int*>(mine + COMM_OFF_AR_EPOCH) = epoch;  // every CTA read it before its arrival above
-        }
-    }
-    comm_wait_flags(c, COMM_OFF_AR_FLAGS, par, epoch, tid);
-    __syncthreads();
-    for (int64_t i = i0 + tid; i < i1; i += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < c.world; r++) s += __ldcg(reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + i);
-        dst[i] = (float)s;
-    }
+    __syncthreads();  // every thread of the CTA has read the epoch
+    if (tid == 0) ar_epoch_arrive(mine, epoch, (unsigned int)G);
+    for (int64_t i = i0 + tid; i < i1; i += blockDim.x) dst[i] = (float)ar_consume(c, par, (size_t)i);
 }
 
 // stand-alone consumer of a fused exchange: dst = f32(sum over ranks of slot[r]) in rank order
@@ -67,13 +51,8 @@ __global__ void __launch_bounds__(256) allreduce_finish_kernel(const CommDev c, 
     const uint8_t* mine = c.peers[c.rank];
     const unsigned int epoch = __ldcg(reinterpret_cast<const unsigned int*>(mine + COMM_OFF_AR_EPOCH));
     const int par = (int)(epoch & 1u);
-    comm_wait_flags(c, COMM_OFF_AR_FLAGS, par, epoch, tid);
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < c.world; r++) s += __ldcg(reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + i);
-        dst[i] = (float)s;
-    }
+    (void)tid;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (float)ar_consume(c, par, (size_t)i);
 }
 
 __global__ void fill_f32_kernel(float* p, int64_t n, float v) {

@@ -4,11 +4,16 @@
 //
 //   producer  = the row-parallel matvec (o_proj / down_proj).  Its flush paths store every finished row sum -- the exact
 //               f64 partial of this rank's K slice -- straight into slot (parity, rank) of EVERY rank's buffer over NVLink
-//               (fire-and-forget peer stores); the last CTA of the launch (device-scope arrival counter after a system
-//               fence) raises this rank's epoch flag at every peer with st.release.sys.
-//   consumer  = the add+RMSNorm+quantise kernel that follows.  It polls the `world` flags in its OWN memory
-//               (ld.acquire.sys), sums the slots in RANK ORDER in f64 and rounds once: identical bits on every rank and
-//               identical to the 1-GPU sum (the partials are exact products accumulated in f64).
+//               (fire-and-forget 8-byte peer stores).  NOTHING ELSE: no fence, no flag.  The all-reduce slots are their own
+//               ready flags (the "LL" idea): they are zero between exchanges, an exact zero is published as -0.0, so
+//               +0.0 bits mean "not written yet" and an aligned 8-byte store is observed whole or not at all.
+//   consumer  = the add+RMSNorm+quantise kernel that follows.  Every thread polls the `world` slot elements of ITS column
+//               in its own memory until all are non-zero, writes +0.0 back (slot free for the exchange after next), sums
+//               them in RANK ORDER in f64 from +0.0 and rounds once: identical bits on every rank and identical to the
+//               1-GPU sum (the partials are exact products accumulated in f64).  An exchange is consumed exactly once.
+//   Round 2 measured the flag form (per-CTA fence.acq_rel.sys + arrival atomic, last CTA raises `world` flags, consumer
+//   acquires them, then loads) at ~13 us per exchange at TP8 -- a system-scope fence waits for every outstanding NVLink store
+//   of the CTA; with self-validating data the exchange costs one NVLink store latency.
 //
 // The same mechanism carries the lm_head all-gather (column-parallel over the vocabulary): f32 logits are stored into
 // region `rank` of every peer's gather area, consumed by the arg-max kernel.  No NCCL, no separate exchange launch.
@@ -20,7 +25,10 @@
 //   [COMM_HDR_BYTES, +2*world*slot_elems*8)        AR slots  f64 [2][world][slot_elems]
 //   [.., + world*gather_elems*4)                   AG region f32 [world][gather_elems]   (initialised to -inf)
 // Two AR slot sets alternate by epoch parity: a rank can run at most one exchange ahead of its slowest peer (it needs
-// that peer's flag of epoch e to finish e), so stores of epoch e+1 never land in a slot a peer is still summing for e.
+// that peer's data of epoch e to finish e), so stores of epoch e+1 never land in a slot a peer is still summing for e, and a
+// peer's stores of epoch e+2 (same parity as e) are issued only after it consumed MY epoch e+1 data, which my stream produces
+// after my consumer of e has zeroed the slots.  The AR epoch is local state: every CTA of a producer reads it, then arrives
+// on the done counter (relaxed, device scope); the last arriver publishes epoch + 1 for the consumer / the next producer.
 // The gather region is single-buffered: 2L all-reduces separate two consecutive lm_heads.
 #pragma once
 #include <stdint.h>
@@ -83,6 +91,45 @@ __device__ __forceinline__ void comm_wait_flags(const CommDev& c, int flags_off,
         }
     }
 }
+// ---- self-validating all-reduce slots ----
+__device__ __forceinline__ double ar_encode(double v) { return v == 0.0 ? -0.0 : v; }   // +0.0 bits are reserved for "empty"
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// producer bookkeeping (tid 0 of every CTA, after the CTA's last use of the epoch): the last arriver advances the epoch
+__device__ __forceinline__ void ar_epoch_arrive(uint8_t* mine, unsigned int epoch, unsigned int n_ctas) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(mine + COMM_OFF_AR_DONE);
+    unsigned int old;
+    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
+    if (old == n_ctas - 1u) {
+        *done = 0u;                                                                     // next launch (ordered by the stream)
+        *reinterpret_cast<unsigned int*>(mine + COMM_OFF_AR_EPOCH) = epoch;
+    }
+}
+// consumer: sum over ranks (rank order, from +0.0) of element idx of the parity-`par` slots; waits for every rank's store and
+// leaves the slots empty.  Bounded spin: a lost peer must not hang the GPU (the result is then garbage, never a deadlock).
+__device__ __forceinline__ double ar_consume(const CommDev& c, int par, size_t idx) {
+    uint8_t* mine = c.peers[c.rank];
+    double v[COMM_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < COMM_MAX_WORLD; r++)
+        if (r < c.world) v[r] = ld_volatile_f64(reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + idx);
+#pragma unroll
+    for (int r = 0; r < COMM_MAX_WORLD; r++)
+        if (r < c.world) {
+            double* q = reinterpret_cast<double*>(mine + comm_ar_slot_off(c, par, r)) + idx;
+            for (int spin = 0; __double_as_longlong(v[r]) == 0ll && spin < (1 << 24); spin++) v[r] = ld_volatile_f64(q);
+            *q = 0.0;
+        }
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < COMM_MAX_WORLD; r++)
+        if (r < c.world) s += v[r];
+    return s;
+}
 #endif
+
 
 }  // namespace b200q

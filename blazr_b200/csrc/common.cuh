@@ -42,6 +42,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// raw 32-bit shared-window addresses (computed once outside hot loops: no per-iteration cvta)
+__device__ __forceinline__ void mbar_wait_sa(uint32_t bar_sa, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_sa), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_sa(uint32_t bar_sa) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar_sa) : "memory");
+}
+
 // ---- bulk async copy global -> shared (TMA engine, 1-D), completion on an mbarrier ----
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
@@ -116,6 +133,37 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
 __device__ __forceinline__ uint2 lds64(const void* p) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
+
+__device__ __forceinline__ uint4 lds128_sa(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64_sa(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32_sa(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16_sa(uint32_t a) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8_sa(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// a lane-constant value the compiler must keep in a register instead of re-deriving it from threadIdx inside a hot loop
+__device__ __forceinline__ uint32_t keep_in_reg(uint32_t v) {
+    asm volatile("" : "+r"(v));
     return v;
 }
 

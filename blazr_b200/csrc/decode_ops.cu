@@ -133,17 +133,12 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
     pdl_wait();
     float v = 0.0f;
     if (c.world > 0) {
-        // the producing matvec of THIS rank completed before the wait returned: its epoch is published; peers may lag
+        // the producing matvec of THIS rank completed before the wait returned: its epoch is published; peers may lag --
+        // every thread waits for the `world` partial sums of its own column (the slots are their own ready flags)
         const uint8_t* mine = c.peers[c.rank];
         const unsigned int epoch = __ldcg(reinterpret_cast<const unsigned int*>(mine + COMM_OFF_AR_EPOCH));
         const int par = (int)(epoch & 1u);
-        comm_wait_flags(c, COMM_OFF_AR_FLAGS, par, epoch, t);
-        __syncthreads();
-        if (active) {
-            double s = 0.0;
-            for (int r = 0; r < c.world; r++) s += __ldcg(reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + (size_t)m * H + k);
-            v = __fadd_rn(h_in[(size_t)m * H + k], (float)s);
-        }
+        if (active) v = __fadd_rn(h_in[(size_t)m * H + k], (float)ar_consume(c, par, (size_t)m * H + k));
     } else if (active) {
         v = h_in[(size_t)m * H + k];
         if (delta) v = __fadd_rn(v, delta[(size_t)m * H + k]);

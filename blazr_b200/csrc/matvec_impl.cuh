@@ -224,7 +224,8 @@ __device__ __forceinline__ void mv_store(const MatvecParams& p, const RpState& r
     if constexpr (!RP) {
         store_out_d(p.y, p.y_dtype, idx, v);
     } else if (p.rp_mode == RP_ALLREDUCE) {
-        for (int r = 0; r < p.comm.world; r++) reinterpret_cast<double*>(p.comm.peers[r] + rp.off)[idx] = v;
+        const double e = ar_encode(v);   // the slot element is its own ready flag (comm_dev.cuh)
+        for (int r = 0; r < p.comm.world; r++) reinterpret_cast<double*>(p.comm.peers[r] + rp.off)[idx] = e;
     } else {
         const float f = (float)v;
         for (int r = 0; r < p.comm.world; r++) reinterpret_cast<float*>(p.comm.peers[r] + rp.off)[idx] = f;
@@ -253,6 +254,24 @@ __device__ __forceinline__ void swiglu_tile_epilogue(const MatvecParams& p, cons
         if (f < p.epi_F) quant_block_to_record(v, p.xq_out + ((size_t)(f / CHUNK_K) * p.epi_rows + rec_row) * ACT_REC_BYTES, (int)((f % CHUNK_K) / 32), lane);
     }
 }
+
+
+// contributors of tile tq under the stream-K split: CTAs gf..gl; sgf = workspace slot (0 head / 1 tail) the first one uses
+__device__ __forceinline__ void sk_tile_span(const MatvecParams& p, int64_t tq, int64_t G, int& gf, int& gl, int& sgf) {
+    if (p.plan32) {
+        gf = (int)((((uint32_t)(tq * p.KC) + 1u) * (uint32_t)G - 1u) / (uint32_t)p.C);
+        gl = (int)((((uint32_t)((tq + 1) * p.KC - 1) + 1u) * (uint32_t)G - 1u) / (uint32_t)p.C);
+        sgf = ((int64_t)sk_begin32((uint32_t)gf, (uint32_t)p.C, (uint32_t)G) == tq * p.KC) ? 0 : 1;
+    } else {
+        gf = (int)sk_owner(tq * p.KC, p.C, G);
+        gl = (int)sk_owner((tq + 1) * p.KC - 1, p.C, G);
+        sgf = (sk_begin(gf, p.C, G) == tq * p.KC) ? 0 : 1;
+    }
+}
+// a split tile with >= MV_WIDE_MIN contributors is reduced by ALL consumer warps of contributor gf + 1 (whose whole chunk range
+// lies inside the tile, so the reduction is the last thing that CTA does): warp w polls contributor gf + w, one L2 round trip
+// for up to 16 contributors instead of one per 4 in the single fix-up warp (measured 4.6 us of tail on 17-way split tiles)
+constexpr int MV_WIDE_MIN = 3;
 
 template <class F, int MB, bool PRO, bool GRP, int OUT>
 __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
@@ -420,18 +439,11 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         for (int seg = 0; seg < 2; seg++) {
             if ((seg == 0 ? sp.nH : sp.nT) == 0) continue;
             const int64_t tq = tqs[seg];
-            int gf, gl;
-            if (p.plan32) {
-                gf = (int)((((uint32_t)(tq * p.KC) + 1u) * (uint32_t)G - 1u) / (uint32_t)p.C);
-                gl = (int)((((uint32_t)((tq + 1) * p.KC - 1) + 1u) * (uint32_t)G - 1u) / (uint32_t)p.C);
-            } else {
-                gf = (int)sk_owner(tq * p.KC, p.C, G);
-                gl = (int)sk_owner((tq + 1) * p.KC - 1, p.C, G);
-            }
+            int gf, gl, sgf;
+            sk_tile_span(p, tq, G, gf, gl, sgf);
             const int nc = gl - gf + 1;
-            const int reducer = nc >= 3 ? gf + 1 : gf;   // a middle contributor finishes at the very end of its life; else the first one
-            if ((int)g != reducer) continue;
-            const int sgf = ((p.plan32 ? (int64_t)sk_begin32((uint32_t)gf, (uint32_t)p.C, (uint32_t)G) : sk_begin(gf, p.C, G)) == tq * p.KC) ? 0 : 1;
+            if (nc >= MV_WIDE_MIN) continue;              // reduced by the consumer warps of contributor gf + 1 (wide reducer)
+            if ((int)g != gf) continue;                   // two contributors: the first one's fix-up warp reduces
             if (MV_TRACE_ON(p) && lane == 0) p.trace[g * 8 + 5] = globaltimer_ns();
             const int64_t tql = GRP ? tq % p.tpw : tq;                      // tile index inside its weight
             const int64_t ybase = GRP ? (tq / p.tpw) * p.y_slot_stride : 0;  // grouped: output of slot tq / tpw
@@ -546,6 +558,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         }
     }
 
+    // am I the wide reducer of my head tile?  (then that segment is my whole range: see MV_WIDE_MIN)
+    bool wide_reducer = false;
+    int wide_gf = 0, wide_gl = 0, wide_sgf = 0;
+    if (sp.nH > 0) {
+        sk_tile_span(p, sp.tH, G, wide_gf, wide_gl, wide_sgf);
+        wide_reducer = (wide_gl - wide_gf + 1) >= MV_WIDE_MIN && (int)g == wide_gf + 1;
+    }
     // segment walk: 0 = head (partial, slot 0), 1 = tail (partial, slot 1), 2 = full tiles
     int kcur = sp.nH > 0 ? sp.kcH : 0;  // k-chunk index of the chunk being processed (fused prologue addressing)
     int seg = sp.nH > 0 ? 0 : (sp.nT > 0 ? 1 : 2);
@@ -554,23 +573,41 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     int s = 0;
     uint32_t ph = 0;
     int n_full_done = 0;  // OUT_SWIGLU: full tiles flushed so far (selects the s_y buffer)
+    // Everything the hot loop addresses is a 32-bit shared-window address built from values computed ONCE here: the ring /
+    // barrier bases and, per lane, the byte offsets of its (row, unit) inside a chunk and of its unit inside an activation
+    // record.  (Left to the compiler, these were re-derived from threadIdx every chunk: ~25 of ~120 instructions per chunk.)
+    constexpr int NOFF = FmtNoff<F>::value;
+    const uint32_t stages_sa = smem_u32(stages), full_sa = keep_in_reg(smem_u32(full)), xhat_sa = smem_u32(xhat);
+    constexpr uint32_t EMPTY_OFF = MV_MAX_STAGES * 8;                     // empty[] follows full[]
+    const uint32_t ring_bytes = (uint32_t)nst * (uint32_t)p.stage_bytes;
+    uint32_t st_off = 0;                                                   // byte offset of stage s inside the ring
+    uint32_t bar_sa = full_sa;                                             // full[s]; empty[s] = + EMPTY_OFF
+    uint32_t uoff[NOFF > 0 ? NOFF : 1];
+    if constexpr (NOFF > 0) {
+        F::unit_offsets(MV_ROWS_PER_WARP * warp + g4, i, meta, uoff);
+#pragma unroll
+        for (int q = 0; q < NOFF; q++) uoff[q] = keep_in_reg(uoff[q] + stages_sa);
+    }
+    const uint32_t xq_off = keep_in_reg((PRO ? xhat_sa : stages_sa + (uint32_t)p.chunk_bytes) + 32u * (uint32_t)i);      // int8 activations of unit i
+    const uint32_t xs_off = keep_in_reg((PRO ? xhat_sa : stages_sa + (uint32_t)p.chunk_bytes) + 256u + 4u * (uint32_t)i); // its scale; + 32: block sums
+    const uint32_t xrec_step = (uint32_t)p.M * ACT_REC_BYTES;
+    uint32_t xk_off = PRO ? (uint32_t)kcur * xrec_step : 0u;               // PRO: record of k-chunk kcur inside xhat
     for (int j = 0; j < n_chunks; j++) {
-        mbar_wait(&full[s], ph);
+        mbar_wait_sa(bar_sa, ph);
         if (MV_TRACE_ON(p) && tid == 0 && j == 0) p.trace[g * 8 + 1] = globaltimer_ns();
         const uint8_t* wc = stages + (size_t)s * p.stage_bytes;
-        const uint8_t* xr = PRO ? xhat + (size_t)kcur * p.M * ACT_REC_BYTES : wc + p.chunk_bytes;
-        if (PRO) { if (++kcur == KC) kcur = 0; }
+        const uint32_t xbase = PRO ? xk_off : st_off;
+        if (PRO) { xk_off += xrec_step; if (++kcur == KC) { kcur = 0; xk_off = 0u; } }
 
         uint4 xa[MB], xb[MB];
         float dx[MB];
         int bsA[MB], bsB[MB];
 #pragma unroll
         for (int m = 0; m < MB; m++) {
-            const uint8_t* rec = xr + m * ACT_REC_BYTES;
-            xa[m] = lds128(rec + 32 * i);
-            xb[m] = lds128(rec + 32 * i + 16);
-            dx[m] = *reinterpret_cast<const float*>(rec + 256 + 4 * i);
-            uint32_t bs = *reinterpret_cast<const uint32_t*>(rec + 288 + 4 * i);
+            xa[m] = lds128_sa(xq_off + xbase + m * ACT_REC_BYTES);
+            xb[m] = lds128_sa(xq_off + xbase + m * ACT_REC_BYTES + 16);
+            dx[m] = __uint_as_float(lds32_sa(xs_off + xbase + m * ACT_REC_BYTES));
+            const uint32_t bs = lds32_sa(xs_off + xbase + m * ACT_REC_BYTES + 32);
             bsA[m] = (int)(int16_t)(bs & 0xFFFFu);
             bsB[m] = (int)(int16_t)(bs >> 16);
         }
@@ -578,9 +615,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         if (!MV_DEBUG_SKIP(p) && !skip_chunk)
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++) {
-            const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
             Unit u;
-            F::template load_unit<true, F::NIB>(wc, r, i, u, meta);
+            if constexpr (NOFF > 0) {
+                if (s4 == 0) F::template load_unit_at<0>(st_off, uoff, i, u, meta);
+                else F::template load_unit_at<1>(st_off, uoff, i, u, meta);
+            } else {
+                const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
+                F::template load_unit<true, F::NIB>(wc, r, i, u, meta);
+            }
 #pragma unroll
             for (int m = 0; m < MB; m++) {
                 int sA = 0, sB = 0;
@@ -610,8 +652,11 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == nst) { s = 0; ph ^= 1u; }
+        if (lane == 0) mbar_arrive_sa(bar_sa + EMPTY_OFF);
+        st_off += (uint32_t)p.stage_bytes;
+        bar_sa += 8u;
+        ++s;
+        if (st_off == ring_bytes) { s = 0; ph ^= 1u; st_off = 0u; bar_sa = full_sa; }
 
         if (--seg_left > 0) continue;
 
@@ -661,7 +706,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 }
             }
         } else {
-            // partial tile: publish my share, then (warp 0) announce the arrival with a release atomic
+            // partial tile: publish my share in my workspace slot (the slot doubles as its own ready flag)
             double* part = p.ws_part + ((size_t)g * 2 + seg) * (TILE_ROWS * MB);
             if (i == 0) {
 #pragma unroll
@@ -675,6 +720,62 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                     }
                 }
             }
+            if (seg == 0 && wide_reducer) {
+                // ---- wide reducer: this CTA's whole range was the head segment; every consumer warp polls one contributor ----
+                constexpr int NT = MV_CONSUMER_WARPS * 32;
+                constexpr int PASSES = 2 * MB;                                  // 64 doubles (one double2 per lane) per pass
+                named_bar_sync(4, NT);                                          // every warp is done with the ring: reuse it
+                if (MV_TRACE_ON(p) && tid == 0) p.trace[g * 8 + 5] = globaltimer_ns();
+                double* red = reinterpret_cast<double*>(stages);                // [wpr][TILE_ROWS * MB]
+                int wpr = (int)(ring_bytes / (uint32_t)(TILE_ROWS * MB * 8));   // contributors per round (ring >= 2 stages >= 36 KB)
+                if (wpr > MV_CONSUMER_WARPS) wpr = MV_CONSUMER_WARPS;
+                double sum = 0.0;
+                for (int base = wide_gf; base <= wide_gl; base += wpr) {
+                    const int gg = base + warp;
+                    if (warp < wpr && gg <= wide_gl) {
+                        double* src = p.ws_part + ((size_t)gg * 2 + (gg == wide_gf ? wide_sgf : 0)) * (TILE_ROWS * MB) + lane * 2;
+                        double2 tb[PASSES];
+                        for (int spin = 0; spin < (1 << 22); spin++) {          // bounded: a lost contributor must not hang the GPU
+                            bool ready = true;
+#pragma unroll
+                            for (int v = 0; v < PASSES; v++) {
+                                asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(tb[v].x), "=d"(tb[v].y) : "l"(src + v * 64));
+                                ready = ready && __double_as_longlong(tb[v].x) != 0ll && __double_as_longlong(tb[v].y) != 0ll;
+                            }
+                            if (__all_sync(0xffffffffu, ready)) break;
+                        }
+#pragma unroll
+                        for (int v = 0; v < PASSES; v++) {
+                            *reinterpret_cast<double2*>(src + v * 64) = make_double2(0.0, 0.0);   // slot free for the next launch
+                            *reinterpret_cast<double2*>(red + (size_t)warp * (TILE_ROWS * MB) + v * 64 + lane * 2) = tb[v];
+                        }
+                    }
+                    named_bar_sync(4, NT);
+                    if (tid < TILE_ROWS * MB) {
+                        const int n_here = (wide_gl - base + 1) < wpr ? (wide_gl - base + 1) : wpr;
+                        for (int w_ = 0; w_ < n_here; w_++) sum += red[(size_t)w_ * (TILE_ROWS * MB) + tid];   // CTA order: deterministic
+                    }
+                    if (base + wpr <= wide_gl) named_bar_sync(4, NT);            // the next round overwrites red[]
+                }
+                const int64_t tql = GRP ? (int64_t)t % p.tpw : (int64_t)t;      // tile index inside its weight
+                const int64_t ybase = GRP ? ((int64_t)t / p.tpw) * p.y_slot_stride : 0;
+                if (tid < TILE_ROWS * MB) {
+                    const double sv = sum == 0.0 ? 0.0 : sum;                   // an exact zero was published as -0.0
+                    const int rr = tid / MB, m = tid % MB;
+                    const int64_t n = tql * TILE_ROWS + rr;
+                    if constexpr (EPI) {
+                        if (m < p.M) s_yfix[m][rr] = (float)(sv + ((p.bias && n < p.N) ? (double)p.bias[n] : 0.0));
+                    } else {
+                        if (n < p.N && m < p.M) mv_store<RP>(p, rp, ybase + (int64_t)m * p.ldy + n, sv + (mv_use_bias<RP>(p) ? (double)p.bias[n] : 0.0));
+                    }
+                }
+                if constexpr (EPI) {
+                    named_bar_sync(4, NT);
+                    if (warp == 0)
+                        for (int m = 0; m < p.M; m++) swiglu_tile_epilogue(p, s_yfix[m], tql, GRP ? (int)(t / p.tpw) : m, lane);
+                }
+                if (MV_TRACE_ON(p) && tid == 0) p.trace[g * 8 + 7] = globaltimer_ns();
+            }
         }
 #pragma unroll
         for (int s4 = 0; s4 < MV_STEPS; s4++)
@@ -682,8 +783,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             for (int m = 0; m < MB; m++) acc[s4][m] = 0.0;
 
         // ---- next segment / tile ----
-        if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; kcur = 0; }
-        else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; kcur = 0; }
+        if (seg == 0 && sp.nT > 0) { seg = 1; seg_left = sp.nT; t = sp.tT; kcur = 0; xk_off = 0u; }
+        else if (seg != 2) { seg = 2; seg_left = KC; t = sp.tF; kcur = 0; xk_off = 0u; }
         else { seg_left = KC; t++; }
 
     }
@@ -692,15 +793,19 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         named_bar_sync(MV_BAR_DONE, MV_CONSUMER_WARPS * 32 + 32);
         if (tid == 0) {
             uint8_t* mine = p.comm.peers[p.comm.rank];
-            const bool ar = p.rp_mode == RP_ALLREDUCE;
-            unsigned int* done = reinterpret_cast<unsigned int*>(mine + (ar ? COMM_OFF_AR_DONE : COMM_OFF_AG_DONE));
-            asm volatile("fence.acq_rel.sys;" ::: "memory");  // the CTA's peer stores (ordered before this thread by the barrier) are performed system-wide
-            unsigned int old;
-            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
-            if (old == (unsigned int)(G - 1)) {
-                *done = 0u;  // next launch (ordered after this one by the stream)
-                comm_raise_flags(p.comm, ar ? COMM_OFF_AR_FLAGS : COMM_OFF_AG_FLAGS, ar ? (int)(rp.epoch & 1u) : 0, rp.epoch);
-                *reinterpret_cast<unsigned int*>(mine + (ar ? COMM_OFF_AR_EPOCH : COMM_OFF_AG_EPOCH)) = rp.epoch;
+            if (p.rp_mode == RP_ALLREDUCE) {
+                // self-validating slots: no fence, no flag -- only the local epoch bookkeeping (last CTA advances it)
+                ar_epoch_arrive(mine, rp.epoch, (unsigned int)G);
+            } else {
+                unsigned int* done = reinterpret_cast<unsigned int*>(mine + COMM_OFF_AG_DONE);
+                asm volatile("fence.acq_rel.sys;" ::: "memory");  // the CTA's peer stores (ordered before this thread by the barrier) are performed system-wide
+                unsigned int old;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
+                if (old == (unsigned int)(G - 1)) {
+                    *done = 0u;  // next launch (ordered after this one by the stream)
+                    comm_raise_flags(p.comm, COMM_OFF_AG_FLAGS, 0, rp.epoch);
+                    *reinterpret_cast<unsigned int*>(mine + COMM_OFF_AG_EPOCH) = rp.epoch;
+                }
             }
         }
     }

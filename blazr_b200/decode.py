@@ -185,10 +185,13 @@ class Decoder:
 
     def __init__(self, client: ops.B200Client, cfg: ModelConfig, scheme: str, batch: int = 1, max_ctx: int = 512,
                  host: Optional[HostModel] = None, seed: int = 0xB200, tp_rank: int = 0, tp_world: int = 1, group=None,
-                 paged: bool = False, block_size: int = 16):
+                 paged: bool = False, block_size: int = 16, emulate_shard: bool = False):
         """paged: KV cache as block pools + block table (reference InferenceConfig.paged_attention / block_size = 16,
         src/config/inference.rs:94-98; forward_with_paged_kv_cache, src/engine/batch_decode.rs:137-147) instead of one
-        contiguous [max_ctx] region per sequence.  The block table is pre-populated with a shuffled assignment of the pool's
+        contiguous [max_ctx] region per sequence.  emulate_shard: build rank tp_rank's shard of a tp_world-way tensor-parallel
+        model but run it ALONE on this GPU through the same fused-exchange kernels (world-1 communicator): the per-rank
+        latency structure of TP-N measured on one GPU (tools / profiling only; the logits are those of the shard).
+        The block table is pre-populated with a shuffled assignment of the pool's
         blocks; a scheduler may overwrite `block_table` / `slot_mapping` between steps (blazr_b200/batch.py builds them)."""
         assert 1 <= batch <= 256
         # M <= 4: dp4a matvec on int8 activation records (bit-exact contract); M > 4 (batched decode, reference
@@ -315,7 +318,10 @@ class Decoder:
         if tp_world > 1 and _os.environ.get("B200Q_TP_NCCL", "0") == "0":
             assert not self.fused and not self.fused_swiglu and self.programs is None and self.step_program is None
             self.vs = tp.vocab_shard_rows(cfg.vocab, tp_world)
-            self.comm = ops.PeerComm(tp_rank, tp_world, M * H, dev, group, gather_elems=M * self.vs)
+            if emulate_shard:
+                self.comm = ops.PeerComm(0, 1, M * H, dev, None, gather_elems=M * self.vs)
+            else:
+                self.comm = ops.PeerComm(tp_rank, tp_world, M * H, dev, group, gather_elems=M * self.vs)
 
     # ---- weights ------------------------------------------------------------------------------------
     def _fused(self, layer: int, parts, K: int, host: Optional[HostModel], kslice=None, interleave: bool = False) -> List[_Linear]:

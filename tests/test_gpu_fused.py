@@ -39,6 +39,32 @@ def test_matmul_norm_equals_norm_then_matvec(client, fmt, K, M):
         assert torch.equal(y, y_ref)
 
 
+@pytest.mark.parametrize("fmt,K,N,M", [("Q4_K", 512, 128 * 350, 1), ("Q4_K", 1024, 128 * 201, 2), ("Q6_K", 2048, 128 * 130, 1), ("Q8_0", 1024, 128 * 263, 4)])
+def test_matmul_norm_stream_k_head_tail_and_full_segments(client, fmt, K, N, M):
+    """more chunks than CTAs with a ragged split: a CTA's range holds a head segment (k-chunks kcH..KC-1 of its first tile), a
+    tail segment (k-chunks 0..nT-1 of its last tile) AND full tiles, so the in-shared-memory activation records are re-walked
+    from k-chunk 0 at every segment switch (regression: the record offset was not rewound after a tail segment)"""
+    t = synth.GGML[fmt]
+    w = client.weight_from_ggml(t, synth.random_ggml(t, N, K, seed=K + M), N, K)
+    g = torch.Generator(device="cuda"); g.manual_seed(K * 3 + M)
+    h_in = torch.randn((M, K), device="cuda", generator=g)
+    delta = torch.randn((M, K), device="cuda", generator=g)
+    wn = 1.0 + 0.1 * torch.randn(K, device="cuda", generator=g)
+    L = ops.lib()
+    P = lambda t_: C.c_void_p(t_.data_ptr())
+    nb = int(L.b200q_act_bytes(C.c_int64(K), C.c_int64(M)))
+    h_ref = torch.empty_like(h_in); xq = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    ops._check(L.b200q_add_rmsnorm_quant(P(h_in), P(delta), P(h_ref), P(wn), C.c_float(1e-5), C.c_int64(K), C.c_int64(M), P(xq), None, None))
+    y_ref = client.matmul_q8(xq, M, w)
+    h_out = torch.zeros_like(h_in); y = torch.zeros((M, N), device="cuda")
+    ws = w.workspace(M)
+    ops._check(L.b200q_matmul_norm(w.handle, P(h_in), P(delta), P(h_out), P(wn), C.c_float(1e-5), C.c_int64(M), P(y),
+                                   C.c_int32(ops.F32), C.c_int64(N), P(ws), C.c_size_t(ws.numel()), None))
+    torch.cuda.synchronize()
+    assert torch.equal(h_out, h_ref)
+    assert torch.equal(y, y_ref)
+
+
 def test_matmul_norm_rejects_unsupported_k(client):
     t = synth.GGML["Q8_0"]
     K = 768  # not 512 * 2^j
