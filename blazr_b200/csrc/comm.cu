@@ -207,7 +207,7 @@ int32_t b200q_allreduce_finish(b200q_comm* c, float* dst, int64_t n, void* strea
     if (!c || !dst || n < 1 || n > c->slot_elems) return set_error(B200Q_ERR_INVALID_ARG, "allreduce_finish: n = %lld outside [1, %lld]", (long long)n, c ? (long long)c->slot_elems : 0ll);
     CommDev d;
     if (!comm_dev(c, &d)) return set_error(B200Q_ERR_INVALID_ARG, "allreduce_finish: communicator not connected");
-    int grid = (int)((n + 1023) / 1024);
+    int grid = (int)((n + 255) / 256);   // one element per thread up to 8192: one round of `world` loads in flight per thread
     if (grid > AR_MAX_CTAS) grid = AR_MAX_CTAS;
     cudaError_t e = launch_pdl_comm(allreduce_finish_kernel, grid, 256, (cudaStream_t)stream, (const CommDev)d, dst, n);
     return e == cudaSuccess ? B200Q_OK : set_error(B200Q_ERR_CUDA, "allreduce_finish launch: %s", cudaGetErrorString(e));

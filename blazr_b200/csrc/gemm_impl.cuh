@@ -226,6 +226,9 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
     if (p.xmc) cluster_sync_all();  // the peer's barriers exist before anything is multicast into this CTA
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    // PDL: the weight stream (static data) starts right away and overlaps the predecessor's tail; only the activation
+    // producer (reads the staged tiles) and the epilogues (write y / the split-K partials) wait for the preceding kernels
+    pdl_launch_dependents();
 
     const int total_tiles = gemm_total(p);
     const int it0 = gemm_first(p), its = gemm_stride(p);
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
     } else if (warp == 2) {
         // ===================== activation tile producer =====================
         if (lane == 0) {
+            pdl_wait();
             int s = 0;
             uint32_t ph = 1;
             const uint32_t half = (uint32_t)p.x_stage_bytes >> 1, hoff = (uint32_t)(blockIdx.x & 1) * half;
@@ -331,6 +335,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
         int acc = 0;
         uint32_t ph0 = 0, ph1 = 0;
+        pdl_wait();  // y / partial may still be read by the preceding kernels
         for (int tile = it0; tile < total_tiles; tile += its) {
             const GemmItem gi = gemm_item(p, tile);
             const int t = gi.t, mt = gi.mt;
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
         const FmtMeta meta{p.gpc};
         int ws = 0, as = 0;
         uint32_t wph = 0, aph = 1, dph = 0;
+        if (!EPI) pdl_wait();  // these warps also run the epilogue (stores to y / partial)
         for (int tile = it0; tile < total_tiles; tile += its) {
             const GemmItem gi = gemm_item(p, tile);
             const int t = gi.t, mt = gi.mt;
@@ -441,26 +447,26 @@ static cudaError_t launch_gemm_dq(const GemmParams& p, int grid, int smem, cudaS
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((4 + DQW + (EPI ? 4 : 0)) * 32);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see the kernel's griddepcontrol placement
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
     if (p.xmc) {  // clusters of two CTAs (adjacent weight tiles, shared activation stages)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3((4 + DQW + (EPI ? 4 : 0)) * 32);
-        cfg.dynamicSmemBytes = (size_t)smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<F, DQW, EPI>, p);
-        count_launch();
-        return le != cudaSuccess ? le : cudaGetLastError();
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
     }
-    gemm_tc_kernel<F, DQW, EPI><<<grid, (4 + DQW + (EPI ? 4 : 0)) * 32, smem, st>>>(p);
+    cfg.attrs = attr;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<F, DQW, EPI>, p);
     count_launch();
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 template <class F>
 static cudaError_t launch_gemm_t(const GemmParams& p, int grid, int smem, cudaStream_t st) {

@@ -11,6 +11,8 @@ namespace b200q {
 // ------------------------------------------------------------------------------------------------
 __global__ void stage_x_kernel(const void* __restrict__ x, int x_dtype, int64_t M, int64_t K, int64_t ldx, const int32_t* __restrict__ perm,
                                int Mt, int KS, uint8_t* __restrict__ xs) {
+    pdl_launch_dependents();
+    pdl_wait();  // x is written by the operator just ahead in the stream
     const int ks = blockIdx.x;
     const int64_t m = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;  // row in padded space
     const int kk = threadIdx.x;                                          // 0..63
@@ -28,6 +30,8 @@ __global__ void stage_x_kernel(const void* __restrict__ x, int x_dtype, int64_t 
 // split-K reduction: y[m,n] = sum_s partial[s][m][n] (+ bias), summed in split order (deterministic)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N, const float* __restrict__ bias, void* y,
                                      int y_dtype, int64_t ldy) {
+    pdl_launch_dependents();
+    pdl_wait();  // the partial sums of the GEMM just ahead
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * N) return;
     const int64_t m = idx / N, n = idx % N;
@@ -39,6 +43,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 // tail split-K reduction: y[m, n] of the tail tiles = sum over splits of partial_tail[tile][s][r][c] (+ bias), split order (deterministic)
 __global__ void splitk_tail_reduce_kernel(const float* __restrict__ partial, int tail_first, int tail_n, int S, int MT, int Mt, int64_t M, int64_t N,
                                           const float* __restrict__ bias, void* y, int y_dtype, int64_t ldy) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, c, r) with r fastest: coalesced along n
     const int64_t per = (int64_t)TILE_ROWS * Mt;
     if (idx >= (int64_t)tail_n * per) return;
@@ -49,6 +55,26 @@ __global__ void splitk_tail_reduce_kernel(const float* __restrict__ partial, int
     float acc = 0.0f;
     for (int s_ = 0; s_ < S; s_++) acc += partial[(((size_t)tl * S + s_) * TILE_ROWS + r) * Mt + c];
     store_out(y, y_dtype, m * ldy + n, acc + (bias ? bias[n] : 0.0f));
+}
+
+
+// every launch of this file carries the programmatic-dependent-launch attribute: the staging / GEMM / reduction kernels of a
+// batched-decode step sit in the same PDL chain as the glue operators (a plain launch would serialise on both of its edges)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_g(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // tail plan of a wide-M launch: (first tail tile, tail tiles, splits); splits == 1 means "no tail split"
@@ -144,9 +170,7 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     {
         dim3 block(64, 4);
         dim3 grid((unsigned)KS, (unsigned)((int64_t)MT * Mt / 4));
-        stage_x_kernel<<<grid, block, 0, st>>>(x, x_dtype, M, w->K, ldx, w->perm, Mt, KS, ws);
-        count_launch();
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_pdl_g(stage_x_kernel, grid, block, 0, st, x, x_dtype, M, w->K, ldx, w->perm, Mt, KS, ws);
         if (e != cudaSuccess) return e;
     }
     // 2. GEMM
@@ -211,16 +235,12 @@ cudaError_t launch_gemm_tc(const b200q_weight* w, const void* x, int x_dtype, in
     ge = gemm_launch_family(w->family, p, grid, smem, st);
     if (ge == cudaSuccess && p.tail_splits > 1) {
         const int64_t total_t = (int64_t)p.tail_n * TILE_ROWS * Mt;
-        splitk_tail_reduce_kernel<<<(unsigned)((total_t + 255) / 256), 256, 0, st>>>(p.partial_tail, p.tail_first, p.tail_n, p.tail_splits, MT, Mt, M, w->N, w->bias,
-                                                                                     y, y_dtype, ldy);
-        count_launch();
-        return cudaGetLastError();
+        return launch_pdl_g(splitk_tail_reduce_kernel, dim3((unsigned)((total_t + 255) / 256)), dim3(256), 0, st, p.partial_tail, p.tail_first, p.tail_n,
+                            p.tail_splits, MT, Mt, M, w->N, w->bias, y, y_dtype, ldy);
     }
     if (ge != cudaSuccess || p.splits == 1) return ge;
     const int64_t total = M * w->N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.splits, M, w->N, w->bias, y, y_dtype, ldy);
-    count_launch();
-    return cudaGetLastError();
+    return launch_pdl_g(splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p.partial, p.splits, M, w->N, w->bias, y, y_dtype, ldy);
 }
 
 }  // namespace b200q

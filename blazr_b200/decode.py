@@ -298,8 +298,14 @@ class Decoder:
         # add+norm+quant fused into the prologue of the matvec that consumes it (b200q_matmul_norm): measured +3..6 % tok/s on one
         # GPU.  Needs hidden = 512 * 2^j <= 8192; tensor parallel keeps the separate kernel (it is the exchange's consumer).
         ept = H // 512
-        self.fused = (_os.environ.get("B200Q_FUSED", "1") != "0" and not self.wide and tp_world == 1 and H % 512 == 0 and ept <= 16
+        # Tensor parallel: the exchange's consumer is the cluster add+norm+quant kernel and plain matvecs follow.  B200Q_TP_FINISH=1
+        # (opt-in) makes the element-wise b200q_allreduce_finish the consumer (delta = f32(sum over ranks)) followed by the same fused
+        # norm-prologue / SwiGLU-epilogue matvecs as on one GPU.  Measured (round 2, 70B Q4_K_M): equal at TP2 (6.21 vs 6.17 ms/step),
+        # SLOWER on the TP8 shard (3.81 vs 3.50 ms): the per-CTA norm prologue (3.6 us) costs more than the cluster kernel saves.
+        self.tp_finish = tp_world > 1 and _os.environ.get("B200Q_TP_FINISH", "0") != "0" and _os.environ.get("B200Q_TP_NCCL", "0") == "0"
+        self.fused = (_os.environ.get("B200Q_FUSED", "1") != "0" and not self.wide and (tp_world == 1 or self.tp_finish) and H % 512 == 0 and ept <= 16
                       and (ept & (ept - 1)) == 0 and not dstep)
+        self.tp_finish = self.tp_finish and self.fused
         self.fused_swiglu = _os.environ.get("B200Q_FUSED_SWIGLU", "0") != "0" and not self.wide  # measured slower: 148x redundant SiLU
         self.pf_bytes = int(float(_os.environ.get("B200Q_PF_MB", "0")) * (1 << 20))
         self.graph = None
@@ -316,7 +322,7 @@ class Decoder:
         # to torch.distributed (NCCL) all-reduce of f32 partials for comparison
         self.comm = None
         if tp_world > 1 and _os.environ.get("B200Q_TP_NCCL", "0") == "0":
-            assert not self.fused and not self.fused_swiglu and self.programs is None and self.step_program is None
+            assert (self.tp_finish or not self.fused) and not self.fused_swiglu and self.programs is None and self.step_program is None
             self.vs = tp.vocab_shard_rows(cfg.vocab, tp_world)
             if emulate_shard:
                 self.comm = ops.PeerComm(0, 1, M * H, dev, None, gather_elems=M * self.vs)
@@ -501,6 +507,9 @@ class Decoder:
         if self.comm is not None:
             assert len(lins) == 1
             self.comm.matmul_q8_rowpar(lins[0].w, xq, self.M, self.cfg.hidden, lins[0].ws)
+            if self.tp_finish:   # element-wise consumer: out = f32(sum over ranks, rank order, f64); the fused-prologue matvec adds + norms it
+                self.comm.allreduce_finish(out)
+                return False
             return True
         self._matvec(lins, xq, out)
         if self.world > 1:
@@ -646,7 +655,8 @@ class Decoder:
                     ops._check(L.b200q_swiglu_quant(P(self.gu), C.c_int64(self.ff), C.c_int64(M), P(self.xq_ff), st))
                 in_flight = self._rowpar(lay["down"], self.xq_ff, self.delta2)
                 delta = self.delta2
-        if fused:
+        head_fused = fused and self.comm is None   # the vocabulary-parallel lm_head (gather form) takes ready-made records
+        if head_fused:
             matvec_norm(self.head, self.final_norm, self.logits_local)
         else:
             norm(self.final_norm)
@@ -656,7 +666,7 @@ class Decoder:
             self.comm.matmul_q8_gather(self.head[0].w, self.xq_h, M, self.vs, self.head[0].ws)
             self.comm.argmax_gathered(self.vs, M, self.ids, self.pos)
             return
-        if not fused:
+        if not head_fused:
             self._matvec(self.head, self.xq_h, self.logits_local)
         if self.world > 1:
             torch.distributed.all_gather_into_tensor(self.logits, self.logits_local, group=self.group)
