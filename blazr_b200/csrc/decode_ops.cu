@@ -17,6 +17,33 @@ namespace b200q {
 // sticky per-device error word raised by kernels that detect an argument they cannot honour without corrupting
 // memory (they write nothing and return); read and cleared by b200q_decode_error()
 __device__ int g_decode_error = 0;
+
+// TRACE builds only (make TRACE=1; tools/trace_step.py): globaltimer stamps of the glue kernels in launch order --
+// record = {kind, entry, after griddepcontrol.wait, exit, 4 phase marks} written by thread 0 of block (0, 0)
+#ifdef B200Q_MV_TRACE
+__device__ long long* g_glue_trace = nullptr;
+__device__ unsigned int g_glue_n = 0;
+__device__ unsigned int g_glue_cap = 0;
+struct GlueTrace {
+    long long* rec;
+    __device__ __forceinline__ GlueTrace(int kind) : rec(nullptr) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && g_glue_trace) {
+            const unsigned int i = atomicAdd(&g_glue_n, 1u);
+            if (i < g_glue_cap) { rec = g_glue_trace + 8 * (size_t)i; rec[0] = kind; rec[1] = globaltimer_ns(); }
+        }
+    }
+    __device__ __forceinline__ void waited() { if (rec) rec[2] = globaltimer_ns(); }
+    __device__ __forceinline__ void done() { if (rec) rec[3] = globaltimer_ns(); }
+    __device__ __forceinline__ void mark(int j) { if (rec) rec[4 + j] = globaltimer_ns(); }   // j < 4: kernel-internal phases
+};
+#else
+struct GlueTrace {
+    __device__ __forceinline__ GlueTrace(int) {}
+    __device__ __forceinline__ void waited() {}
+    __device__ __forceinline__ void done() {}
+    __device__ __forceinline__ void mark(int) {}
+};
+#endif
 constexpr int B200Q_DECODE_ERR_POSITION = 1;  // attention: pos[m] outside [0, max_ctx)
 
 // ---- shared: quantise 256 values held one per thread (thread t <-> k = kc*256 + t) into a record ----
@@ -66,6 +93,7 @@ constexpr int NORM_NT = 1024;  // one float4 of the row per thread for H = 4096:
 __global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float* __restrict__ h_in, const float* __restrict__ delta,
                                                                      float* __restrict__ h_out, const float* __restrict__ w, float eps, int H, int M,
                                                                      uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
+    GlueTrace gt(3);
     pdl_launch_dependents();
     const int kc = blockIdx.x, m = blockIdx.y, t = threadIdx.x;
     const float* hr = h_in + (size_t)m * H;
@@ -73,6 +101,7 @@ __global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float*
     __shared__ double red[NORM_NT / 32];
     const float wk = (t < CHUNK_K) ? w[kc * CHUNK_K + t] : 0.0f;  // static weights: fetched before the dependency wait
     pdl_wait();
+    gt.waited();
     // f64: exact squares, order-independent sum -> bit-reproducible against the oracle (4 independent chains)
     float mine = 0.0f;
     if (t < CHUNK_K) {
@@ -105,6 +134,7 @@ __global__ void __launch_bounds__(NORM_NT) add_rmsnorm_quant_kernel(const float*
     const float v = __fmul_rn(__fmul_rn(mine, inv), wk);
     if (xnorm) xnorm[(size_t)m * H + k] = v;
     if (xq) quant_store_record(v, xq + ((size_t)kc * M + m) * ACT_REC_BYTES, t);
+    gt.done();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,6 +152,7 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
                                                                              uint8_t* __restrict__ xq, float* __restrict__ xnorm) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
+    GlueTrace gt(2);
     pdl_launch_dependents();
     const int cta = blockIdx.x, ncta = gridDim.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int k = cta * NORMC_NT + t;
@@ -131,18 +162,41 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
     __shared__ float s_inv;
     const float wk = active ? w[k] : 0.0f;  // static weights: fetched before the dependency wait
     pdl_wait();
+    gt.waited();
     float v = 0.0f;
-    if (c.world > 0) {
-        // the producing matvec of THIS rank completed before the wait returned: its epoch is published; peers may lag --
-        // every thread waits for the `world` partial sums of its own column (the slots are their own ready flags)
-        const uint8_t* mine = c.peers[c.rank];
+    double* zslot = nullptr;   // TP: this thread's element of the rank-0 slot of the consumed parity (emptied after the cluster barrier)
+    if (c.world > 0 && active) {   // (threads beyond the row take no part: they must never poll an element another thread empties)
+        // The producing matvec of THIS rank completed before the wait returned (its epoch is published); peers may lag: every
+        // thread waits for the `world` partial sums of its own column -- the slots are their own ready flags (comm_dev.cuh).
+        // ONE L2 round trip: the epoch and this column's slot elements of BOTH parities are requested together; the parity
+        // that is not being exchanged is empty or stale and simply ignored.
+        uint8_t* mine = c.peers[c.rank];
+        const size_t idx = (size_t)m * H + (size_t)k;
+        double sv[2][COMM_MAX_WORLD];
         const unsigned int epoch = __ldcg(reinterpret_cast<const unsigned int*>(mine + COMM_OFF_AR_EPOCH));
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++)
+#pragma unroll
+            for (int r = 0; r < COMM_MAX_WORLD; r++)
+                if (r < c.world) sv[pr][r] = ld_volatile_f64(reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, pr, r)) + idx);
+        const float hv = h_in[(size_t)m * H + k];
         const int par = (int)(epoch & 1u);
-        if (active) v = __fadd_rn(h_in[(size_t)m * H + k], (float)ar_consume(c, par, (size_t)m * H + k));
-    } else if (active) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < COMM_MAX_WORLD; r++)
+            if (r < c.world) {
+                double x = par ? sv[1][r] : sv[0][r];
+                const double* q = reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + idx;
+                for (int spin = 0; __double_as_longlong(x) == 0ll && spin < (1 << 24); spin++) x = ld_volatile_f64(q);   // bounded: a lost peer must not hang the GPU
+                s += x;   // rank order, from +0.0 (an exact zero travels as -0.0)
+            }
+        zslot = reinterpret_cast<double*>(mine + comm_ar_slot_off(c, par, 0)) + idx;
+        v = __fadd_rn(hv, (float)s);
+    } else if (c.world <= 0 && active) {
         v = h_in[(size_t)m * H + k];
         if (delta) v = __fadd_rn(v, delta[(size_t)m * H + k]);
     }
+    gt.mark(0);   // inputs (all ranks' partial sums) are in registers
     double ss = (double)v * (double)v;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -154,14 +208,24 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
         if (lane == 0) cta_part = p;
     }
+    gt.mark(1);
     cluster.sync();
+    gt.mark(2);
     if (warp == 0) {
+        // lane r fetches CTA r's share (ONE distributed-shared-memory latency instead of ncta dependent ones: measured 1.4 us
+        // between the cluster barrier and the stores in round 2), then the shares are summed in CTA order: identical on every CTA
+        double mine_part = 0.0;
+        if (lane < ncta) mine_part = *cluster.map_shared_rank(&cta_part, lane);
         double tot = 0.0;
-        for (int r = 0; r < ncta; r++) tot += *cluster.map_shared_rank(&cta_part, r);  // CTA order: identical on every CTA
+        for (int r = 0; r < ncta; r++) tot += __shfl_sync(0xffffffffu, mine_part, r);
         if (lane == 0) s_inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn((float)tot, (float)H), eps)));
     }
-    // a CTA's shared memory must stay alive until its peers have read cta_part: arrive now, wait only before exiting
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    // a CTA's shared memory must stay alive until its peers have read cta_part: arrive now, wait only before exiting.
+    // .relaxed: this barrier orders execution only (no data is handed over), so it does not wait for the global stores below
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    if (zslot) {   // the consumed slots are free for the exchange after next (issued here: off the barrier's release path)
+        for (int r = 0; r < c.world; r++) zslot[(size_t)r * (size_t)c.slot_elems] = 0.0;
+    }
     __syncthreads();  // s_inv
     if (active) {
         h_out[(size_t)m * H + k] = v;
@@ -169,7 +233,9 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
         if (xnorm) xnorm[(size_t)m * H + k] = x;
         if (xq) quant_store_record(x, xq + ((size_t)(k / CHUNK_K) * M + m) * ACT_REC_BYTES, k % CHUNK_K);
     }
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    gt.mark(3);   // outputs stored
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    gt.done();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -216,6 +282,7 @@ template <int HD, bool PAGED>
 __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ pos, float* __restrict__ cache_k,
                                                            float* __restrict__ cache_v, const float* __restrict__ rope, int nh, int nkv,
                                                            int max_ctx, int M, uint8_t* __restrict__ xq, float* __restrict__ attn_out, const PagedKv pg) {
+    GlueTrace gt(1);
     pdl_launch_dependents();
     extern __shared__ float s_sc[];  // scores, then probabilities, for positions 0..p
     const int head = blockIdx.x, m = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -275,6 +342,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
         if (t < HD / 2) { rc = rt[2 * t]; rs = rt[2 * t + 1]; }
     }
     pdl_wait();
+    gt.waited();
     if (bad_pos) {
         if (t == 0) atomicOr(&g_decode_error, B200Q_DECODE_ERR_POSITION);
         return;
@@ -396,6 +464,7 @@ __global__ void __launch_bounds__(ATT_NT) attn_decode_kernel(const float* __rest
             reinterpret_cast<float*>(rec + 256)[tin >> 5] = d;
             reinterpret_cast<uint32_t*>(rec + 288)[tin >> 5] = ((uint32_t)s & 0xFFFFu) | ((uint32_t)s_hi << 16);
         }
+        gt.done();
     }
 }
 
@@ -667,6 +736,22 @@ int32_t b200q_decode_error(int32_t* out_flags) {
     }
     *out_flags = v;
     return B200Q_OK;
+}
+
+/* TRACE builds (make TRACE=1) only: dev_buf receives {kind, entry, after-wait, exit, 4 phase marks} globaltimer records (8 x int64 each) of
+ * the glue kernels in launch order, up to `cap` records; null stops the trace.  kind: 1 attention, 2 cluster add+norm, 3 add+norm */
+int32_t b200q_debug_set_glue_trace(void* dev_buf, int32_t cap) {
+#ifdef B200Q_MV_TRACE
+    long long* p = (long long*)dev_buf;
+    unsigned int zero = 0, c = dev_buf ? (unsigned int)cap : 0u;
+    if (cudaMemcpyToSymbol(g_glue_trace, &p, sizeof(p)) != cudaSuccess) return B200Q_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_glue_n, &zero, sizeof(zero)) != cudaSuccess) return B200Q_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_glue_cap, &c, sizeof(c)) != cudaSuccess) return B200Q_ERR_CUDA;
+    return B200Q_OK;
+#else
+    (void)dev_buf; (void)cap;
+    return B200Q_ERR_UNSUPPORTED;
+#endif
 }
 
 int32_t b200q_argmax(const float* logits, int64_t V, int64_t M, int64_t* out_ids, int32_t* pos_inc, void* stream) {

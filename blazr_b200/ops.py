@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200q.so")
+LIB_PATH = os.environ.get("B200Q_LIB") or os.path.join(_HERE, "lib", "libb200q.so")   # B200Q_LIB: e.g. the TRACE build (csrc/Makefile)
 
 F32, F16, BF16, F64 = 0, 1, 2, 3
 _TORCH2DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float64: F64}

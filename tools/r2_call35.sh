@@ -1,0 +1,8 @@
+#!/bin/bash
+# TRACE library (blazr_b200/lib/libb200q_trace.so): in-graph timeline (matvec + glue kernels) of several configs, raw stamps kept
+mkdir -p gpurun_out
+export B200Q_LIB=$PWD/blazr_b200/lib/libb200q_trace.so
+B200Q_TRACE_DUMP=gpurun_out/r2_trace_tp8emu.npz B200Q_EMULATE_TP=8 timeout 300 python tools/trace_step.py --workload llama-3-70b:Q4_K_M --layers 1 2>&1 | grep -v Warn > gpurun_out/r2_trace_step_70b_tp8emu_c.log; tail -12 gpurun_out/r2_trace_step_70b_tp8emu_c.log
+B200Q_TRACE_DUMP=gpurun_out/r2_trace_tp1.npz timeout 300 python tools/trace_step.py --workload llama-3-70b:Q4_K_M --layers 1 2>&1 | grep -v Warn > gpurun_out/r2_trace_step_70b_tp1_c.log; tail -9 gpurun_out/r2_trace_step_70b_tp1_c.log
+B200Q_TRACE_DUMP=gpurun_out/r2_trace_7b.npz timeout 300 python tools/trace_step.py --workload mistral-7b:Q4_K --layers 1 2>&1 | grep -v Warn > gpurun_out/r2_trace_step_7b.log; tail -7 gpurun_out/r2_trace_step_7b.log
+B200Q_TRACE_DUMP=gpurun_out/r2_trace_1b.npz timeout 300 python tools/trace_step.py --workload llama-3.2-1b:Q4_K_M --layers 1 2>&1 | grep -v Warn > gpurun_out/r2_trace_step_1b.log; tail -7 gpurun_out/r2_trace_step_1b.log
