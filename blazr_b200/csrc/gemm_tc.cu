@@ -103,6 +103,9 @@ static int pick_splits(const b200q_weight* w, int MT, int64_t M) {
     int smax = 8;
     if (smax > (int)w->KC / 2) smax = (int)w->KC / 2;
     if (smax < 1) smax = 1;
+    // tuning knob (skinny launches only): B200Q_GEMM_SPLITS forces the split-K factor (clamped to [1, KC / 2])
+    static const int forced = [] { const char* e_ = getenv("B200Q_GEMM_SPLITS"); return e_ ? atoi(e_) : 0; }();
+    if (forced > 0 && M <= 128) return forced > smax ? smax : forced;
     if (M > 128) {
         int s = (int)(sms / tiles);
         if (s > smax) s = smax;

@@ -122,6 +122,7 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.gate_up = fp ? fp->gate_up : nullptr;
     p.w_table = nullptr;
     p.sel = nullptr;
+    p.n_experts = 0;
     p.tpw = (int)w->T;
     p.x_rows = (int)M;
     p.x_slot_div = 1;
@@ -201,6 +202,7 @@ cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, i
     p.stage_bytes = plan.stage_bytes;
     p.w_table = b->table_dev;
     p.sel = sel_dev;
+    p.n_experts = b->E;
     p.tpw = (int)b->proto.T;
     p.x_rows = (int)x_rows;
     p.x_slot_div = (int)x_slot_div;

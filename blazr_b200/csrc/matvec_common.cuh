@@ -64,6 +64,7 @@ struct MatvecParams {
     int plan32;     // (C + 1) * G < 2^32: the stream-K plan is computed with 32-bit divisions
     const uint8_t* const* w_table;
     const int32_t* sel;
+    int n_experts;        // grouped: entries of w_table; a selection outside [0, n_experts) is treated as "not hosted" (slot skipped)
     int tpw;              // tiles per weight
     int x_rows, x_slot_div;
     int64_t y_slot_stride;

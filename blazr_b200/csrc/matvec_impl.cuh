@@ -194,6 +194,16 @@ __device__ __forceinline__ void fused_prologue(const MatvecParams& p, uint8_t* x
     named_bar_sync(4, NT);  // records visible to every consumer warp
 }
 
+// int32 -> f64.  -DB200Q_MV_MAGIC_I2D: without the conversion unit -- the double with high word 0x43300000 and low word
+// (s ^ 0x80000000) is 2^52 + 2^31 + s exactly, one DADD (FP64 pipe) removes the bias -- instead of I2F.F64 (XU pipe, 8 issue
+// cycles per warp instruction, 3-4 per chunk).  Measured in round 2: NEUTRAL (Q4_K gate|up 15.69 vs 15.59 us, 70B step 108.7 vs
+// 109.7 tok/s): the XU pipe (24-26 % busy) is not what paces the consumer loop.  Kept as a compile-time experiment.
+#ifdef B200Q_MV_MAGIC_I2D
+__device__ __forceinline__ double i2d(int s) { return __hiloint2double(0x43300000, (int)((unsigned)s ^ 0x80000000u)) - 4503601774854144.0; }
+#else
+__device__ __forceinline__ double i2d(int s) { return (double)s; }
+#endif
+
 // Per-CTA globaltimer trace and the "skip the math" debug flag cost ~6 instructions per chunk in the consumer loop: they are
 // compiled in only with -DB200Q_MV_TRACE (make TRACE=1; tools/trace_matvec.py, tools/trace_step.py need that build).
 #ifdef B200Q_MV_TRACE
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 if (!grouped) return p.w + vc * (int64_t)wbytes;
                 const int64_t slot = vc / cpw;
                 const int e = p.sel[slot];
-                return e < 0 ? nullptr : p.w_table[e] + (vc - slot * cpw) * (int64_t)wbytes;
+                return (e < 0 || e >= p.n_experts) ? nullptr : p.w_table[e] + (vc - slot * cpw) * (int64_t)wbytes;   // never index past the bank
             };
             auto chunk_x = [&](int j) -> const uint8_t* {
                 int kc;
@@ -640,13 +650,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
                 sB -= u.off[1] * bsB[m];
                 double a_ = acc[s4][m];
                 if (F::SUB == 32) {  // one scale per 32 weights
-                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), (double)(sA + sB), a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), (double)(bsA[m] + bsB[m]), a_);
+                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), i2d(sA + sB), a_);
+                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), i2d(bsA[m] + bsB[m]), a_);
                 } else {             // two 16-wide sub-blocks with their own scales
-                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), (double)sA, a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), (double)bsA[m], a_);
-                    a_ = fma((double)__fmul_rn(u.a[1], dx[m]), (double)sB, a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[1], dx[m]), (double)bsB[m], a_);
+                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), i2d(sA), a_);
+                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), i2d(bsA[m]), a_);
+                    a_ = fma((double)__fmul_rn(u.a[1], dx[m]), i2d(sB), a_);
+                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[1], dx[m]), i2d(bsB[m]), a_);
                 }
                 acc[s4][m] = a_;
             }

@@ -196,10 +196,11 @@ int32_t b200q_moe_combine(const float* y, const float* gate_w, int64_t T, int64_
  * all-reduce blazr's TP issues after the row-parallel o_proj / down_proj, reference src/engine/tensor_parallel.rs:125-163;
  * SURVEY.md sections 5 and 8b/8e).  One process per GPU: create on every rank, all-gather the 64-byte IPC handles, connect.
  *   producer  b200q_matmul_q8_rowpar : the row-parallel matvec stores its exact f64 row sums [M, ld] straight into a slot of
- *             every rank's buffer (peer stores from the kernel's flush paths); its last CTA raises the epoch flags.
- *   consumer  b200q_allreduce_add_rmsnorm_quant : polls the flags in local memory, sums the `world` slots in rank order in
- *             f64, rounds once (identical bits on every rank and equal to the 1-GPU output), adds the residual, RMS-norms and
- *             quantises -- the reduced vector never exists in HBM and the exchange costs no launch of its own.
+ *             every rank's buffer (8-byte peer stores from the kernel's flush paths) and nothing else: the slot elements are
+ *             their own ready flags (empty = +0.0 bits; an exact zero travels as -0.0), no fence, no flag, no extra launch.
+ *   consumer  b200q_allreduce_add_rmsnorm_quant : every thread polls the `world` slot elements of its column in local memory,
+ *             empties them, sums in rank order in f64, rounds once (identical bits on every rank and equal to the 1-GPU
+ *             output), adds the residual, RMS-norms and quantises -- the reduced vector never exists in HBM.
  *             b200q_allreduce_finish is the stand-alone consumer (reduced f32 vector) for other callers.
  *   lm_head   b200q_matmul_q8_gather (column-parallel over the vocabulary) stores f32 logits [M, ld] into region `rank` of
  *             every rank's gather area; b200q_argmax_gathered consumes them (vocabulary id = rank * ld + column).
