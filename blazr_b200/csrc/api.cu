@@ -377,6 +377,20 @@ int32_t b200q_weight_set_next(b200q_weight* w, const b200q_weight* next) {
     return B200Q_OK;
 }
 
+int32_t b200q_weight_set_pair(b200q_weight* w, const b200q_weight* second) {
+    if (!w) return fail(B200Q_ERR_INVALID_ARG, "null weight");
+    if (!second) { w->pair = nullptr; return B200Q_OK; }
+    if (second == w || second->pair) return fail(B200Q_ERR_INVALID_ARG, "a weight cannot be paired with itself or with a weight that has a partner");
+    if (second->device != w->device) return fail(B200Q_ERR_INVALID_ARG, "partner lives on device %d, weight on device %d", second->device, w->device);
+    if (second->K != w->K || second->KC != w->KC) return fail(B200Q_ERR_INVALID_ARG, "partner K = %lld differs from K = %lld", (long long)second->K, (long long)w->K);
+    if (w->N % TILE_ROWS) return fail(B200Q_ERR_UNSUPPORTED, "the first weight of a pair needs N %% 128 == 0 (got %lld): its partner's rows follow it tile-aligned", (long long)w->N);
+    if (w->bias || second->bias || w->perm || second->perm) return fail(B200Q_ERR_UNSUPPORTED, "paired weights carry neither a bias nor an act-order permutation");
+    if (!(w->family == B200Q_FAM_Q4_K && second->family == B200Q_FAM_Q6_K))
+        return fail(B200Q_ERR_UNSUPPORTED, "dual-format launch is built for a Q4_K weight followed by a Q6_K one (families %d, %d)", w->family, second->family);
+    w->pair = second;
+    return B200Q_OK;
+}
+
 // ---- compute ----
 size_t b200q_act_bytes(int64_t K, int64_t M) {
     int64_t kc = (K + CHUNK_K - 1) / CHUNK_K;

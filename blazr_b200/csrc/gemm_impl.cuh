@@ -15,6 +15,7 @@
 //   * warp roles: 0 = weight-chunk producer, 2 = activation producer, 1 = TMEM allocator + single-thread
 //     MMA issuer, 4..11 = dequant (8 warps) + epilogue (tcgen05.ld -> bias -> global).
 #pragma once
+#include <atomic>
 #include "formats.cuh"
 #include "internal.h"
 
@@ -439,13 +440,13 @@ __global__ void __launch_bounds__((4 + DQW + (EPI ? 4 : 0)) * 32, 1) gemm_tc_ker
 
 template <class F, int DQW, bool EPI>
 static cudaError_t launch_gemm_dq(const GemmParams& p, int grid, int smem, cudaStream_t st) {
-    static bool configured[16] = {false};
+    static std::atomic<bool> configured[16];   // per device; racing first calls both set the attribute (idempotent): re-entrant
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
+    if (dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F, DQW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 16) configured[dev].store(true, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

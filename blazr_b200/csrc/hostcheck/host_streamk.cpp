@@ -11,6 +11,7 @@ using namespace b200q;
 //  1 chunk not covered exactly once            2 a CTA's segments do not add up to its range
 //  3 the consumer walk flushes a wrong tile    4 fix-up contributor range / count / slot mismatch
 //  5 a tile flagged "full" is not owned by one CTA      6 the 32-bit plan differs from the 64-bit plan
+//  7 the wide reducer's CTA (contributor gf + 1 of a tile with >= 3 contributors) owns chunks outside that tile
 extern "C" int streamk_check(int64_t T, int64_t KC, int64_t G_in, int64_t* n_split_tiles, int64_t* max_contrib) {
     const int64_t C = T * KC;
     int64_t G = G_in > C ? C : G_in;   // matvec_plan clamps the grid to the chunk count
@@ -93,6 +94,16 @@ extern "C" int streamk_check(int64_t T, int64_t KC, int64_t G_in, int64_t* n_spl
             for (auto& pr : cs)
                 if (pr.first == g && pr.second == want_slot) found = true;
             if (!found) return 4;
+        }
+        // wide reducer (matvec_impl.cuh, MV_WIDE_MIN = 3): with three or more contributors the tile is reduced by ALL consumer
+        // warps of contributor gf + 1 after its last chunk -- valid only if that CTA's whole chunk range lies inside this tile
+        // (its head segment is all it owns: nothing else to compute, the weight ring is dead and can hold the partials)
+        if (nc >= 3) {
+            const int64_t g = gf + 1;
+            const int64_t c0 = sk_begin(g, C, G), c1 = sk_begin(g + 1, C, G);
+            const SkPlan sp = sk_plan(c0, c1, KC);
+            if (c0 < tq * KC || c1 > (tq + 1) * KC) return 7;
+            if (sp.nH != (int)(c1 - c0) || sp.nT != 0 || sp.nF != 0 || sp.tH != (int)tq) return 7;
         }
     }
     if (n_split_tiles) *n_split_tiles = nsplit;

@@ -17,6 +17,7 @@ struct b200q_weight {
     int32_t* perm;  // device i32 [K] (GPTQ act-order) or null
     int num_sms;
     const b200q_weight* next;  // successor hint (b200q_weight_set_next), not owned; null = none
+    const b200q_weight* pair;  // dual-format partner (b200q_weight_set_pair), not owned: its rows follow this weight's in y; null = none
 };
 
 // Expert bank (boostr::ExpertWeights stacked [num_experts, ...]): E weights of one format and shape

@@ -51,10 +51,15 @@ static long long* g_trace = nullptr;
 static int g_trace_launch = 0;
 void set_matvec_trace(long long* p) { g_trace = p; g_trace_launch = 0; }
 
+// dual-format partner honoured by a launch: plain / norm-prologue matvecs only (not the SwiGLU, grouped or fused-exchange forms)
+static const b200q_weight* dual_partner(const b200q_weight* w) { return w->pair; }
+
 cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int pro) {
     if (M < 1 || M > 4) return cudaErrorInvalidValue;
     int mb = M == 1 ? 1 : (M == 2 ? 2 : 4);
-    int stage = w->chunk_bytes + (pro ? 0 : (int)M * ACT_REC_BYTES);
+    const b200q_weight* w2 = dual_partner(w);
+    const int cbmax = (w2 && w2->chunk_bytes > w->chunk_bytes) ? w2->chunk_bytes : w->chunk_bytes;
+    int stage = cbmax + (pro ? 0 : (int)M * ACT_REC_BYTES);
     stage = (stage + 127) & ~127;
     int xhat = pro ? (int)(((size_t)w->KC * M * ACT_REC_BYTES + 127) & ~(size_t)127) : 0;
     // > half an SM on purpose: two CTAs of one launch must never share an SM (measured: after glue kernels perturb
@@ -67,7 +72,7 @@ cudaError_t matvec_plan(const b200q_weight* w, int64_t M, MatvecPlan* plan, int 
     if (nst > MV_MAX_STAGES) nst = MV_MAX_STAGES;
     if (const char* e = getenv("B200Q_MV_STAGES")) { int v = atoi(e); if (v >= 2 && v < nst) nst = v; }
     if (nst < 2) return cudaErrorInvalidValue;
-    int64_t C = w->T * w->KC;
+    int64_t C = (w->T + (w2 ? w2->T : 0)) * w->KC;
     int64_t G = (int64_t)w->num_sms;
     if (const char* e = getenv("B200Q_MV_GRID")) { int v = atoi(e); if (v >= 1 && v <= w->num_sms) G = v; }  // ws_part holds num_sms slots
     if (G > C) G = C;
@@ -92,6 +97,9 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
                           const FusedPrologue* fp, const RemoteOut* ro, void* swiglu_xq_out) {
     MatvecPlan plan;
     const int pro = fp ? fp->mode : 0;
+    const b200q_weight* w2 = dual_partner(w);
+    // a paired weight is launched together with its partner, by the plain / norm-prologue forms only; y holds N1 + N2 columns
+    if (w2 && (ro || swiglu_xq_out || (fp && fp->mode != 1) || ldy < w->N + w2->N)) return cudaErrorInvalidValue;
     cudaError_t e = matvec_plan(w, M, &plan, pro);
     if (e != cudaSuccess) return e;
     MatvecParams p;
@@ -102,15 +110,20 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     size_t cnt = ((size_t)w->T * 4 + 255) & ~(size_t)255;
     p.ws_cnt = reinterpret_cast<unsigned int*>(ws);
     p.ws_part = reinterpret_cast<double*>(ws + cnt);
-    p.N = w->N;
+    p.N = w->N + (w2 ? w2->N : 0);       // dual: rows of w2 follow (N1 % 128 == 0, checked by b200q_weight_set_pair)
     p.M = (int)M;
     p.y_dtype = y_dtype;
     p.ldy = ldy;
     p.KC = w->KC;
-    p.C = w->T * w->KC;
+    p.C = (w->T + (w2 ? w2->T : 0)) * w->KC;
     p.gpc = w->gpc;
     p.nstages = plan.nstages;
-    p.chunk_bytes = w->chunk_bytes;
+    p.chunk_bytes = (w2 && w2->chunk_bytes > w->chunk_bytes) ? w2->chunk_bytes : w->chunk_bytes;
+    p.cb1 = w->chunk_bytes;
+    p.cb2 = w2 ? w2->chunk_bytes : 0;
+    p.w2 = w2 ? w2->data : nullptr;
+    p.T1 = (int)w->T;
+    p.gpc2 = w2 ? w2->gpc : 0;
     p.stage_bytes = plan.stage_bytes;
     p.pro = pro;
     p.xhat_bytes = plan.xhat_bytes;
@@ -123,7 +136,7 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
     p.w_table = nullptr;
     p.sel = nullptr;
     p.n_experts = 0;
-    p.tpw = (int)w->T;
+    p.tpw = (int)(w->T + (w2 ? w2->T : 0));
     p.x_rows = (int)M;
     p.x_slot_div = 1;
     p.y_slot_stride = 0;
@@ -164,6 +177,11 @@ cudaError_t launch_matvec(const b200q_weight* w, const uint8_t* xq, int64_t M, v
         if (const char* e = getenv("B200Q_MV_L2PF")) p.l2_prefetch_chunks = atoi(e);
     }
     if (const char* e = getenv("B200Q_MV_DEBUG")) p.debug_flags = atoi(e);
+    if (w2) {
+        p.next_w = nullptr; p.next_pf = 0;
+        if (w->family == B200Q_FAM_Q4_K && w2->family == B200Q_FAM_Q6_K) return mv_launch_dual_q4k_q6k(p, plan.mb, plan.grid, plan.smem_bytes, st);
+        return cudaErrorInvalidValue;
+    }
     return launch_family(w->family, p, plan.mb, plan.grid, plan.smem_bytes, st);
 }
 
@@ -203,6 +221,7 @@ cudaError_t launch_matvec_grouped(const b200q_bank* b, const int32_t* sel_dev, i
     p.w_table = b->table_dev;
     p.sel = sel_dev;
     p.n_experts = b->E;
+    p.w2 = nullptr; p.cb1 = v.chunk_bytes; p.cb2 = 0; p.T1 = 0; p.gpc2 = 0;
     p.tpw = (int)b->proto.T;
     p.x_rows = (int)x_rows;
     p.x_slot_div = (int)x_slot_div;

@@ -62,6 +62,13 @@ struct MatvecParams {
     int epi_F;      // rows of gate (= rows of up) = N / 2
     int epi_rows;   // record rows per k-chunk: M (plain) or n_slots (grouped)
     int plan32;     // (C + 1) * G < 2^32: the stream-K plan is computed with 32-bit divisions
+    // dual-format launch (kernel template F2 != F; b200q_weight_set_pair): a second weight of another format whose output rows
+    // directly follow the first one's (y2 = y + N1, N1 % 128 == 0) rides in the same stream-K grid -- tiles [0, T1) belong to w
+    // (format F, cb1 bytes per chunk), tiles [T1, T1 + T2) to w2 (format F2, cb2 bytes per chunk).  chunk_bytes is then the
+    // larger of the two: the offset of the activation records inside a ring stage.  One launch instead of two for the q|k + v
+    // projections of Q4_K_M files (V is Q6_K in about half of the layers).
+    const uint8_t* w2;
+    int cb1, cb2, T1, gpc2;
     const uint8_t* const* w_table;
     const int32_t* sel;
     int n_experts;        // grouped: entries of w_table; a selection outside [0, n_experts) is treated as "not hosted" (slot skipped)
@@ -73,5 +80,7 @@ struct MatvecParams {
 // per-format launcher, defined (explicitly specialised) in inst_<format>.cu so formats compile in parallel
 template <int FAMILY>
 cudaError_t mv_launch(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st);
+// dual-format launcher (inst_q4k_q6k.cu): first weight Q4_K, second Q6_K
+cudaError_t mv_launch_dual_q4k_q6k(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st);
 
 }  // namespace b200q

@@ -13,6 +13,8 @@
 //     through per-CTA partial slots in the workspace: the last CTA to arrive (atomic counter) sums the
 //     partials in CTA order and writes y (no float atomics, no inter-CTA waiting).
 #pragma once
+#include <atomic>
+#include <type_traits>
 #include "matvec_common.cuh"
 
 namespace b200q {
@@ -283,10 +285,12 @@ __device__ __forceinline__ void sk_tile_span(const MatvecParams& p, int64_t tq, 
 // for up to 16 contributors instead of one per 4 in the single fix-up warp (measured 4.6 us of tail on 17-way split tiles)
 constexpr int MV_WIDE_MIN = 3;
 
-template <class F, int MB, bool PRO, bool GRP, int OUT>
+template <class F, int MB, bool PRO, bool GRP, int OUT, class F2 = F>
 __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParams p) {
     constexpr bool RP = OUT == OUT_REMOTE;
     constexpr bool EPI = OUT == OUT_SWIGLU;
+    constexpr bool DUAL = !std::is_same<F, F2>::value;   // two weights of different formats in one grid (MatvecParams::w2)
+    static_assert(!DUAL || (!GRP && OUT == OUT_PLAIN), "the dual-format launch is a plain matvec");
     __shared__ float s_y[EPI ? 2 : 1][EPI ? MB : 1][EPI ? TILE_ROWS : 1];   // finished full tiles (double-buffered)
     __shared__ float s_yfix[EPI ? MB : 1][EPI ? TILE_ROWS : 1];             // finished split tile (fix-up warp only)
     extern __shared__ __align__(128) uint8_t smem[];
@@ -334,8 +338,12 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             const uint32_t xbytes0 = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
             const int pre0 = n_chunks < nst ? n_chunks : nst;
             for (int j = 0; j < pre0; j++) {
-                mbar_arrive_expect_tx(&full[j], (uint32_t)p.chunk_bytes + xbytes0);
-                bulk_g2s_hint(stages + (size_t)j * p.stage_bytes, p.w + sk_chunk_at(spp, c0, j) * (int64_t)p.chunk_bytes, (uint32_t)p.chunk_bytes, &full[j], pol0);
+                const int64_t vc0 = sk_chunk_at(spp, c0, j);
+                const uint8_t* src0 = p.w + vc0 * (int64_t)p.cb1;
+                uint32_t wb0 = (uint32_t)p.cb1;
+                if (DUAL && vc0 >= (int64_t)p.T1 * p.KC) { src0 = p.w2 + (vc0 - (int64_t)p.T1 * p.KC) * (int64_t)p.cb2; wb0 = (uint32_t)p.cb2; }
+                mbar_arrive_expect_tx(&full[j], wb0 + xbytes0);
+                bulk_g2s_hint(stages + (size_t)j * p.stage_bytes, src0, wb0, &full[j], pol0);
             }
         }
     }
@@ -347,7 +355,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
             const uint32_t xbytes = PRO ? 0u : (uint32_t)p.M * ACT_REC_BYTES;
-            const uint32_t wbytes = (uint32_t)p.chunk_bytes;
+            const uint32_t wbytes = (uint32_t)p.cb1;              // bytes of one chunk of w (dual: chunks of w2 have cb2, see chunk_src)
+            const uint32_t xoff_in_stage = (uint32_t)p.chunk_bytes;  // offset of the activation records inside a stage
             constexpr bool grouped = GRP;  // expert-bank launch (compile-time: the plain matvec carries none of it)
             const int64_t cpw = (int64_t)p.tpw * p.KC;  // grouped: chunks per weight
             if (grouped) pdl_wait();                      // the expert selection is produced by the preceding kernel
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             };
             auto chunk_src = [&](int j) -> const uint8_t* {
                 const int64_t vc = chunk_vc(j);
+                if (DUAL && vc >= (int64_t)p.T1 * p.KC) return p.w2 + (vc - (int64_t)p.T1 * p.KC) * (int64_t)p.cb2;
                 if (!grouped) return p.w + vc * (int64_t)wbytes;
                 const int64_t slot = vc / cpw;
                 const int e = p.sel[slot];
@@ -381,15 +391,16 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             // copy, a flag behind the stage's activation record tells the consumers to leave the accumulators at zero
             auto issue_w = [&](int j, uint8_t* st, uint64_t* bar) {
                 const uint8_t* src = chunk_src(j);
+                const uint32_t wb = (DUAL && chunk_vc(j) >= (int64_t)p.T1 * p.KC) ? (uint32_t)p.cb2 : wbytes;
                 if (grouped) {
                     const bool skip = src == nullptr;
                     *reinterpret_cast<volatile int*>(st + wbytes + xbytes) = skip ? 1 : 0;
                     mbar_arrive_expect_tx(bar, (skip ? 0u : wbytes) + xbytes);
                     if (skip) return;
                 } else {
-                    mbar_arrive_expect_tx(bar, wbytes + xbytes);
+                    mbar_arrive_expect_tx(bar, wb + xbytes);
                 }
-                bulk_g2s_hint(st, src, wbytes, bar, pol);
+                bulk_g2s_hint(st, src, wb, bar, pol);
             };
             if (GRP)  // (the plain forms requested their first ring-full ahead of the CTA barrier)
                 for (int j = 0; j < pre; j++) issue_w(j, stages + (size_t)j * p.stage_bytes, &full[j]);
@@ -401,14 +412,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             if (MV_TRACE_ON(p)) p.trace[g * 8 + 4] = globaltimer_ns();
             if (!PRO)
                 for (int j = 0; j < pre; j++)
-                    bulk_g2s(stages + (size_t)j * p.stage_bytes + wbytes, chunk_x(j), xbytes, &full[j]);
+                    bulk_g2s(stages + (size_t)j * p.stage_bytes + xoff_in_stage, chunk_x(j), xbytes, &full[j]);
             int s = 0;
             uint32_t ph = 0;  // second use of each stage waits for the consumers' first release (phase 0)
             for (int j = pre; j < n_chunks; j++) {
                 mbar_wait(&empty[s], ph);
                 uint8_t* st = stages + (size_t)s * p.stage_bytes;
                 issue_w(j, st, &full[s]);
-                if (!PRO) bulk_g2s(st + wbytes, chunk_x(j), xbytes, &full[s]);
+                if (!PRO) bulk_g2s(st + xoff_in_stage, chunk_x(j), xbytes, &full[s]);
                 if (++s == nst) { s = 0; ph ^= 1u; }
             }
             // every chunk of this launch is requested: keep HBM busy with the successor's first chunks (L2 prefetch)
@@ -598,6 +609,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
 #pragma unroll
         for (int q = 0; q < NOFF; q++) uoff[q] = keep_in_reg(uoff[q] + stages_sa);
     }
+    constexpr int NOFF2 = DUAL ? FmtNoff<F2>::value : 0;   // dual-format launch: the second weight's lane offsets
+    const FmtMeta meta2{p.gpc2};
+    uint32_t uoff2[NOFF2 > 0 ? NOFF2 : 1];
+    if constexpr (NOFF2 > 0) {
+        F2::unit_offsets(MV_ROWS_PER_WARP * warp + g4, i, meta2, uoff2);
+#pragma unroll
+        for (int q = 0; q < NOFF2; q++) uoff2[q] = keep_in_reg(uoff2[q] + stages_sa);
+    }
     const uint32_t xq_off = keep_in_reg((PRO ? xhat_sa : stages_sa + (uint32_t)p.chunk_bytes) + 32u * (uint32_t)i);      // int8 activations of unit i
     const uint32_t xs_off = keep_in_reg((PRO ? xhat_sa : stages_sa + (uint32_t)p.chunk_bytes) + 256u + 4u * (uint32_t)i); // its scale; + 32: block sums
     const uint32_t xrec_step = (uint32_t)p.M * ACT_REC_BYTES;
@@ -622,43 +641,55 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
             bsB[m] = (int)(int16_t)(bs >> 16);
         }
         const bool skip_chunk = GRP && *reinterpret_cast<const volatile int*>(wc + p.chunk_bytes + p.M * ACT_REC_BYTES) != 0;
-        if (!MV_DEBUG_SKIP(p) && !skip_chunk)
+        // the units of this chunk: rows 8 warp + 4 s4 + g4, unit i -- format FF (dual-format launches pick it per tile)
+        auto chunk_math = [&](auto tag, const auto& uo, const FmtMeta& mt) {
+            using FF = decltype(tag);
+            constexpr int NO = FmtNoff<FF>::value;
 #pragma unroll
-        for (int s4 = 0; s4 < MV_STEPS; s4++) {
-            Unit u;
-            if constexpr (NOFF > 0) {
-                if (s4 == 0) F::template load_unit_at<0>(st_off, uoff, i, u, meta);
-                else F::template load_unit_at<1>(st_off, uoff, i, u, meta);
-            } else {
-                const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
-                F::template load_unit<true, F::NIB>(wc, r, i, u, meta);
-            }
-#pragma unroll
-            for (int m = 0; m < MB; m++) {
-                int sA = 0, sB = 0;
-                sA = __dp4a((int)u.v[0], (int)xa[m].x, sA); sA = __dp4a((int)u.v[1], (int)xa[m].y, sA);
-                sA = __dp4a((int)u.v[2], (int)xa[m].z, sA); sA = __dp4a((int)u.v[3], (int)xa[m].w, sA);
-                if constexpr (F::NIB) {  // bytes hold 16 x q (unsigned): exact u8 x s8 dot, one arithmetic shift back
-                    sB = dp4a_us(u.v[4], xb[m].x, sB); sB = dp4a_us(u.v[5], xb[m].y, sB);
-                    sB = dp4a_us(u.v[6], xb[m].z, sB); sB = dp4a_us(u.v[7], xb[m].w, sB);
-                    sB >>= 4;
+            for (int s4 = 0; s4 < MV_STEPS; s4++) {
+                Unit u;
+                if constexpr (NO > 0) {
+                    if (s4 == 0) FF::template load_unit_at<0>(st_off, uo, i, u, mt);
+                    else FF::template load_unit_at<1>(st_off, uo, i, u, mt);
                 } else {
-                    sB = __dp4a((int)u.v[4], (int)xb[m].x, sB); sB = __dp4a((int)u.v[5], (int)xb[m].y, sB);
-                    sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
+                    const int r = MV_ROWS_PER_WARP * warp + 4 * s4 + g4;
+                    FF::template load_unit<true, FF::NIB>(wc, r, i, u, mt);
                 }
-                sA -= u.off[0] * bsA[m];
-                sB -= u.off[1] * bsB[m];
-                double a_ = acc[s4][m];
-                if (F::SUB == 32) {  // one scale per 32 weights
-                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), i2d(sA + sB), a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), i2d(bsA[m] + bsB[m]), a_);
-                } else {             // two 16-wide sub-blocks with their own scales
-                    a_ = fma((double)__fmul_rn(u.a[0], dx[m]), i2d(sA), a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), i2d(bsA[m]), a_);
-                    a_ = fma((double)__fmul_rn(u.a[1], dx[m]), i2d(sB), a_);
-                    if (F::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[1], dx[m]), i2d(bsB[m]), a_);
+#pragma unroll
+                for (int m = 0; m < MB; m++) {
+                    int sA = 0, sB = 0;
+                    sA = __dp4a((int)u.v[0], (int)xa[m].x, sA); sA = __dp4a((int)u.v[1], (int)xa[m].y, sA);
+                    sA = __dp4a((int)u.v[2], (int)xa[m].z, sA); sA = __dp4a((int)u.v[3], (int)xa[m].w, sA);
+                    if constexpr (FF::NIB) {  // bytes hold 16 x q (unsigned): exact u8 x s8 dot, one arithmetic shift back
+                        sB = dp4a_us(u.v[4], xb[m].x, sB); sB = dp4a_us(u.v[5], xb[m].y, sB);
+                        sB = dp4a_us(u.v[6], xb[m].z, sB); sB = dp4a_us(u.v[7], xb[m].w, sB);
+                        sB >>= 4;
+                    } else {
+                        sB = __dp4a((int)u.v[4], (int)xb[m].x, sB); sB = __dp4a((int)u.v[5], (int)xb[m].y, sB);
+                        sB = __dp4a((int)u.v[6], (int)xb[m].z, sB); sB = __dp4a((int)u.v[7], (int)xb[m].w, sB);
+                    }
+                    sA -= u.off[0] * bsA[m];
+                    sB -= u.off[1] * bsB[m];
+                    double a_ = acc[s4][m];
+                    if (FF::SUB == 32) {  // one scale per 32 weights
+                        a_ = fma((double)__fmul_rn(u.a[0], dx[m]), i2d(sA + sB), a_);
+                        if (FF::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), i2d(bsA[m] + bsB[m]), a_);
+                    } else {             // two 16-wide sub-blocks with their own scales
+                        a_ = fma((double)__fmul_rn(u.a[0], dx[m]), i2d(sA), a_);
+                        if (FF::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[0], dx[m]), i2d(bsA[m]), a_);
+                        a_ = fma((double)__fmul_rn(u.a[1], dx[m]), i2d(sB), a_);
+                        if (FF::HAS_MIN) a_ = fma(-(double)__fmul_rn(u.b[1], dx[m]), i2d(bsB[m]), a_);
+                    }
+                    acc[s4][m] = a_;
                 }
-                acc[s4][m] = a_;
+            }
+        };
+        if (!MV_DEBUG_SKIP(p) && !skip_chunk) {
+            if constexpr (DUAL) {
+                if (t >= p.T1) chunk_math(F2{}, uoff2, meta2);   // warp-uniform: a tile belongs to one weight
+                else chunk_math(F{}, uoff, meta);
+            } else {
+                chunk_math(F{}, uoff, meta);
             }
         }
         __syncwarp();
@@ -822,15 +853,15 @@ __global__ void __launch_bounds__(MV_THREADS, 1) matvec_kernel(const MatvecParam
     if (MV_TRACE_ON(p) && tid == 0) p.trace[g * 8 + 3] = globaltimer_ns();
 }
 
-template <class F, int MB, bool PRO, bool GRP, int OUT = OUT_PLAIN>
+template <class F, int MB, bool PRO, bool GRP, int OUT = OUT_PLAIN, class F2 = F>
 static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStream_t st) {
-    static bool configured[16] = {false};
+    static std::atomic<bool> configured[16];   // per device; racing first calls both set the attribute (idempotent): re-entrant
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + static shared memory (epilogue tiles, reductions) <= 227 KB
+    if (dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(matvec_kernel<F, MB, PRO, GRP, OUT, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);  // + static shared memory (epilogue tiles, reductions) <= 227 KB
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 16) configured[dev].store(true, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -842,10 +873,22 @@ static cudaError_t launch_t(const MatvecParams& p, int grid, int smem, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP, OUT>, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, matvec_kernel<F, MB, PRO, GRP, OUT, F2>, p);
     if (le != cudaSuccess) return le;
     count_launch();
     return cudaGetLastError();
+}
+
+// dual-format launch (MatvecParams::w2): plain output, optional norm prologue
+template <class F, class F2>
+static cudaError_t launch_dual(const MatvecParams& p, int mb, int grid, int smem, cudaStream_t st) {
+    if (p.w_table || p.rp_mode != RP_NONE || p.xq_out || !p.w2) return cudaErrorInvalidValue;
+    switch (mb) {
+        case 1: return p.pro ? launch_t<F, 1, true, false, OUT_PLAIN, F2>(p, grid, smem, st) : launch_t<F, 1, false, false, OUT_PLAIN, F2>(p, grid, smem, st);
+        case 2: return p.pro ? launch_t<F, 2, true, false, OUT_PLAIN, F2>(p, grid, smem, st) : launch_t<F, 2, false, false, OUT_PLAIN, F2>(p, grid, smem, st);
+        case 4: return p.pro ? launch_t<F, 4, true, false, OUT_PLAIN, F2>(p, grid, smem, st) : launch_t<F, 4, false, false, OUT_PLAIN, F2>(p, grid, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 template <class F>

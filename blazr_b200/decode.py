@@ -177,6 +177,7 @@ class _Linear:
     w: ops.QuantWeight
     col0: int
     ws: torch.Tensor
+    fmt: str = ""
 
 
 class Decoder:
@@ -231,6 +232,14 @@ class Decoder:
             lay["qkv"] = self._fused(i, [("q", fm["q"], cfg.n_heads * hd, pl.q_rows[0], self.qd),
                                          ("k", fm["k"], cfg.n_kv_heads * hd, pl.kv_rows[0], self.kvd),
                                          ("v", fm["v"], cfg.n_kv_heads * hd, pl.kv_rows[0], self.kvd)], H, host)
+            # decode matvecs (M <= 4): a Q4_K q|k group followed by a Q6_K v (Q4_K_M files: about half of the layers) is ONE
+            # dual-format launch (b200q_weight_set_pair) instead of two; the tcgen05 paths keep the separate launches
+            lay["qkv_mv"] = lay["qkv"]
+            qk = lay["qkv"]
+            if (len(qk) == 2 and not self.wide and not dstep and _os.environ.get("B200Q_DUAL", "1") != "0" and qk[0].w.N % 128 == 0
+                    and (qk[0].fmt, qk[1].fmt) == ("Q4_K", "Q6_K")):
+                qk[0].w.set_pair(qk[1].w)
+                lay["qkv_mv"] = [qk[0]]
             # row-parallel o: K slice = this rank's heads
             lay["o"] = self._fused(i, [("o", fm["o"], H, 0, H)], cfg.n_heads * hd, host, kslice=pl.o_cols)
             lay["swiglu_epi"] = self.swiglu_epi_wanted and fm["gate"] == fm["up"] and fm["gate"] in synth.GGML
@@ -346,7 +355,7 @@ class Decoder:
             nrows = sum(p[4] for p in grp)
             w = self._upload(layer, grp, fmt, K, host, kslice, interleave=interleave)
             self.weight_bytes += w.canonical_bytes
-            out.append(_Linear(w, col, w.workspace(self.M)))
+            out.append(_Linear(w, col, w.workspace(self.M), fmt))
             col += nrows
         return out
 
@@ -614,10 +623,10 @@ class Decoder:
         fused = self.fused
         for li, lay in enumerate(self.layers):
             if fused:
-                matvec_norm(lay["qkv"], lay["attn_norm"], self.qkv)
+                matvec_norm(lay["qkv_mv"], lay["attn_norm"], self.qkv)
             else:
                 norm(lay["attn_norm"])
-                self._matvec(lay["qkv"], self.xq_h, self.qkv)
+                self._matvec(lay["qkv_mv"], self.xq_h, self.qkv)
             self._attention(lay, st)
             in_flight = self._rowpar(lay["o"], self.xq_attn, self.delta)
             delta = self.delta

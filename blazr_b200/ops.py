@@ -51,7 +51,7 @@ class WeightInfo(C.Structure):
 EXPORTS = [
     "b200q_version", "b200q_last_error", "b200q_device_count", "b200q_weight_from_ggml", "b200q_weight_from_ggml_shard",
     "b200q_weight_from_awq", "b200q_weight_from_gptq", "b200q_weight_from_awq_shard", "b200q_weight_from_gptq_shard", "b200q_weight_free", "b200q_weight_info",
-    "b200q_weight_set_bias", "b200q_weight_set_next", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
+    "b200q_weight_set_bias", "b200q_weight_set_next", "b200q_weight_set_pair", "b200q_shard_range", "b200q_shard_range_blocks", "b200q_workspace_bytes", "b200q_matmul",
     "b200q_act_bytes", "b200q_quantize_act", "b200q_matmul_q8", "b200q_matmul_path", "b200q_dequantize", "b200q_act_unpack",
     "b200q_int_partials", "b200q_launch_count", "b200q_add_rmsnorm_quant", "b200q_swiglu_quant", "b200q_attn_decode", "b200q_attn_decode_paged",
     "b200q_argmax", "b200q_decode_error", "b200q_embed", "b200q_weight_prefetch_l2", "b200q_matmul_norm", "b200q_matmul_swiglu",
@@ -170,12 +170,19 @@ class QuantWeight:
         _check(lib().b200q_weight_set_next(self._h, nxt.handle if nxt is not None else None))
         self._next = nxt
 
+    def set_pair(self, second: Optional["QuantWeight"]):
+        """dual-format pairing (include/b200q.h b200q_weight_set_pair): decode matvecs on this weight also compute `second`
+        (another format, same K) into the columns that follow this weight's.  A reference is kept so the pairing cannot dangle."""
+        _check(lib().b200q_weight_set_pair(self._h, second.handle if second is not None else None))
+        self._pair = second
+
     def free(self):
         if self._h is not None:
             lib().b200q_weight_free(self._h)
             self._h = None
             self._ws = {}
             self._next = None
+            self._pair = None
 
     def __del__(self):
         try:

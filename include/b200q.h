@@ -129,6 +129,14 @@ int32_t b200q_weight_set_bias(b200q_weight* w, const float* bias, int32_t src_on
  * so HBM keeps streaming across the kernel boundary and the glue operators in between.  `next` is not owned: clear the
  * hint (next = NULL) before freeing it.  The one mutable field of a handle; set it before the handle is shared. */
 int32_t b200q_weight_set_next(b200q_weight* w, const b200q_weight* next);
+/* Dual-format pairing: `second` (same K, same device, no bias / permutation) is a projection of ANOTHER format that reads the same
+ * activations as `w` and whose output columns directly follow w's (y[:, N1 : N1 + N2], N1 % 128 == 0) -- the q|k (Q4_K) and v
+ * (Q6_K) projections of a Q4_K_M file (reference src/loader/gguf.rs:365-372 tags every tensor with its own ggml type).  Every decode
+ * matvec on `w` (b200q_matmul_q8 / b200q_matmul_norm, M <= 4) then computes BOTH in one launch: ldy and the output buffer must
+ * cover N1 + N2 columns; the fused-exchange, SwiGLU and tcgen05 (M >= 5) forms refuse / ignore the pairing.  Built for Q4_K + Q6_K;
+ * other combinations return B200Q_ERR_UNSUPPORTED (launch them separately).  `second` is not owned: clear the pairing
+ * (second = NULL) before freeing it.  Set it before the handle is shared. */
+int32_t b200q_weight_set_pair(b200q_weight* w, const b200q_weight* second);
 
 /* reference src/engine/tensor_parallel.rs:61-67 */
 int32_t b200q_shard_range(int64_t total, int64_t rank, int64_t world, int64_t* start, int64_t* end);

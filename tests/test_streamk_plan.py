@@ -1,7 +1,8 @@
 """CPU check of the matvec kernel's stream-K plan (blazr_b200/csrc/streamk_plan.cuh, compiled for the host): for every
 grid size and (tiles, k-chunks) combination -- including every projection shape of the BASELINE configs at TP 1/2/4/8 and
 the grouped MoE launches -- each chunk is streamed exactly once, the consumer walk flushes the tile it accumulated, and
-the fix-up's contributor range / count / partial-slot bookkeeping matches the CTAs that really contribute."""
+the fix-up's contributor range / count / partial-slot bookkeeping matches the CTAs that really contribute, and the wide
+reducer's premise holds (contributor gf + 1 of a tile split three or more ways owns chunks of that tile only)."""
 import ctypes as C
 import os
 import subprocess

@@ -13,7 +13,7 @@ dec = (decode.Decoder(client, decode.PRESETS[model], scheme, batch=1, max_ctx=25
        else decode.Decoder(client, decode.PRESETS[model], scheme, batch=1, max_ctx=256))
 dec.reset([1]); dec.pos.fill_(48)
 dec.step(); torch.cuda.synchronize()
-n_launch = sum(len(l["qkv"]) + len(l["o"]) + len(l["gu"]) + len(l["down"]) for l in dec.layers) + len(dec.head)
+n_launch = sum(len(l["qkv_mv"]) + len(l["o"]) + len(l["gu"]) + len(l["down"]) for l in dec.layers) + len(dec.head)
 # capture() first runs the step eagerly (launch indices 0 .. n_launch-1), then captures it (n_launch .. 2 n_launch - 1): the
 # graph replays stamp the SECOND half (round 2's first version read the eager half: CPU launch gaps, not the graph's timeline)
 trace = torch.zeros(2 * n_launch * 148 * 8, dtype=torch.int64, device="cuda")
@@ -42,9 +42,9 @@ if os.environ.get("B200Q_TRACE_DUMP"):   # raw stamps for offline analysis (int6
 # launch order of the matvec kernels inside one step (mixed-format groups are several launches)
 names = []
 for li, l in enumerate(dec.layers):
-    for key in ("qkv", "o", "gu", "down"):
+    for key in ("qkv_mv", "o", "gu", "down"):
         for j, _ in enumerate(l[key]):
-            names.append((li, key if len(l[key]) == 1 else f"{key}{j}"))
+            names.append((li, key.replace("_mv", "") if len(l[key]) == 1 else f"{key.replace('_mv', '')}{j}"))
 names += [(-1, "head")] * len(dec.head)
 t0 = None
 prev_exit = None
