@@ -1,5 +1,6 @@
 #!/bin/bash
-# FINAL build: full GPU suite, default bench with extras, filtered launch list of the default decode step
+# One gpurun call that validates a build on ONE B200: full GPU suite, default bench with extras, filtered launch list of the default
+# decode step, the reference (CPU) arm.  gpurun --timeout 2400 -- "bash tools/final_validate.sh"; multi-GPU: tools/r2_tp.sh N
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider 2>&1 | tail -4 | tee gpurun_out/r2_pytest_gpu_final.tail
 timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench exit $?"; tail -2 gpurun_out/r2_bench_final.err
