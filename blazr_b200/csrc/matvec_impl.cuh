@@ -10,8 +10,12 @@
 //     256-k chunk (unit i = 32 consecutive k), 4 rows per step; activations stay in registers for the
 //     8 rows; integer dot products with dp4a, per-sub-block scales applied in f32;
 //   * at tile end an 8-lane shuffle reduction; tiles split between CTAs are combined DETERMINISTICALLY
-//     through per-CTA partial slots in the workspace: the last CTA to arrive (atomic counter) sums the
-//     partials in CTA order and writes y (no float atomics, no inter-CTA waiting).
+//     through per-CTA partial slots in the workspace that double as their own ready flags (+0.0 bits = empty):
+//     two contributors -> the first one's fix-up warp polls and sums beside the consumers; three or more ->
+//     all 16 consumer warps of contributor gf + 1 poll one contributor each (MV_WIDE_MIN); always CTA order,
+//     no float atomics;
+//   * compile-time variants: norm prologue (PRO), SwiGLU epilogue / fused tensor-parallel exchange (OUT),
+//     grouped expert-bank launch (GRP), dual-format launch (F2 != F: two weights of different formats, one grid).
 #pragma once
 #include <atomic>
 #include <type_traits>
