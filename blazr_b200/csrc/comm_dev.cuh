@@ -36,6 +36,9 @@
 namespace b200q {
 
 constexpr int COMM_MAX_WORLD = 8;
+// Consumers poll a slot element at most this many times (one L2 round trip each, ~0.5 us: about a minute) before giving up:
+// ranks may be seconds apart at the first exchange after a load, but a lost peer must not hang the GPU for ever.
+constexpr int COMM_SPIN_LIMIT = 1 << 27;
 constexpr size_t COMM_HDR_BYTES = 8192;
 constexpr int COMM_OFF_AR_FLAGS = 0;
 constexpr int COMM_OFF_AG_FLAGS = 256;
@@ -120,7 +123,7 @@ __device__ __forceinline__ double ar_consume(const CommDev& c, int par, size_t i
     for (int r = 0; r < COMM_MAX_WORLD; r++)
         if (r < c.world) {
             double* q = reinterpret_cast<double*>(mine + comm_ar_slot_off(c, par, r)) + idx;
-            for (int spin = 0; __double_as_longlong(v[r]) == 0ll && spin < (1 << 24); spin++) v[r] = ld_volatile_f64(q);
+            for (int spin = 0; __double_as_longlong(v[r]) == 0ll && spin < COMM_SPIN_LIMIT; spin++) v[r] = ld_volatile_f64(q);
             *q = 0.0;
         }
     double s = 0.0;

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(NORMC_NT) add_rmsnorm_quant_cluster_kernel(con
             if (r < c.world) {
                 double x = par ? sv[1][r] : sv[0][r];
                 const double* q = reinterpret_cast<const double*>(mine + comm_ar_slot_off(c, par, r)) + idx;
-                for (int spin = 0; __double_as_longlong(x) == 0ll && spin < (1 << 24); spin++) x = ld_volatile_f64(q);   // bounded: a lost peer must not hang the GPU
+                for (int spin = 0; __double_as_longlong(x) == 0ll && spin < COMM_SPIN_LIMIT; spin++) x = ld_volatile_f64(q);   // bounded: a lost peer must not hang the GPU
                 s += x;   // rank order, from +0.0 (an exact zero travels as -0.0)
             }
         zslot = reinterpret_cast<double*>(mine + comm_ar_slot_off(c, par, 0)) + idx;
